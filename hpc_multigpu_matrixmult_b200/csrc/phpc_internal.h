@@ -1,0 +1,65 @@
+/* phpc_internal.h — shared by the translation units of libphpc_b200.so (not installed). */
+#pragma once
+#include <cublas_v2.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define PHPC_B200_VERSION 100
+
+#define PHPC_MAX_DEVICES 16
+
+[[noreturn]] void phpc_die(const char *what, const char *detail, const char *file, int line);
+
+#define CUDA_CHECK(call)                                                           \
+  do {                                                                             \
+    cudaError_t err__ = (call);                                                    \
+    if (err__ != cudaSuccess) phpc_die(#call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+  } while (0)
+
+#define CUBLAS_CHECK(call)                                                \
+  do {                                                                    \
+    cublasStatus_t st__ = (call);                                         \
+    if (st__ != CUBLAS_STATUS_SUCCESS) {                                  \
+      char msg__[64];                                                     \
+      snprintf(msg__, sizeof msg__, "cublas status %d", (int)st__);       \
+      phpc_die(#call, msg__, __FILE__, __LINE__);                         \
+    }                                                                     \
+  } while (0)
+
+#define PHPC_REQUIRE(cond, msg)                                  \
+  do {                                                           \
+    if (!(cond)) phpc_die(#cond, msg, __FILE__, __LINE__);       \
+  } while (0)
+
+/* grow-only cached device buffer (the reference cudaMallocAsync/cudaFreeAsync's
+ * three buffers on every k-step, src/phpc_gemm.cu:106-108,123-125) */
+struct DevBuf {
+  void *ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct DeviceCtx {
+  bool ready = false;
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t compute = nullptr; /* GEMM launches */
+  cudaStream_t comm = nullptr;    /* NCCL broadcasts (high priority) */
+  cudaStream_t copy = nullptr;    /* H2D / D2H staging */
+  cublasHandle_t blas = nullptr;
+  unsigned int *sched = nullptr; /* tile-scheduler words, self-resetting */
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DevBuf bufA, bufB, bufC;
+};
+
+DeviceCtx *phpc_ctx(int device); /* lazily created; makes `device` current */
+DeviceCtx *phpc_cur_ctx(void);   /* context of the process' bound device */
+void *phpc_buf_reserve(DevBuf *b, size_t bytes);
+
+/* enqueue the DMMA kernel on `stream`; returns launches (0 or 1) */
+int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
+                     int k, int n, int ctas, cudaStream_t stream);
+void phpc_launch_cublas(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
+                        int k, int n, cudaStream_t stream);
+
+static inline long long phpc_pad_ld(long long cols) { return (cols + 15) / 16 * 16; }

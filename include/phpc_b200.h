@@ -1,0 +1,83 @@
+/*
+ * phpc_b200.h — ADDITIONS to the reference's C interface (nothing here replaces a
+ * reference symbol; phpc_gemm.cuh and phpc_summa.h hold the drop-in entry points
+ * and are implemented on top of these).  Plain C ABI: pointers, sizes, ints.
+ *
+ * Device-resident entry points exist because the reference's host-pointer API
+ * (src/phpc_gemm.cu:93-121: pin, cudaMallocAsync, H2D, kernel, D2H, free on
+ * EVERY k-step) cannot express "operands already in HBM", which is where a B200
+ * SUMMA keeps them (decision D3).
+ *
+ * All functions abort the process with a message on CUDA/NCCL/cuBLAS errors.
+ */
+#ifndef _PHPC_B200_H
+#define _PHPC_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library / device ---------------------------------------------------- */
+/* Library ABI version (also proves the .so loads without a GPU). */
+int phpc_b200_version(void);
+/* Number of visible CUDA devices; 0 when there is no driver/GPU (never aborts). */
+int phpc_b200_device_count(void);
+/* Bind the calling process to `device` (one process per GPU); creates the
+ * per-device context (streams, cuBLAS handle, tile-scheduler words). */
+void phpc_b200_set_device(int device);
+int phpc_b200_get_device(void);
+int phpc_b200_sm_count(void);
+/* Release every cached device buffer, stream and handle. */
+void phpc_b200_finalize(void);
+
+/* ---- memory -------------------------------------------------------------- */
+void *phpc_device_malloc(size_t bytes);
+void phpc_device_free(void *p);
+void *phpc_host_malloc_pinned(size_t bytes);
+void phpc_host_free_pinned(void *p);
+void phpc_device_memset(void *p, int value, size_t bytes);
+void phpc_device_synchronize(void);
+
+/* ---- local block GEMM on device pointers --------------------------------- */
+/*
+ * dC[m x n, ldc] += dA[m x k, lda] * dB[k x n, ldb] with the sm_100a DMMA kernel,
+ * enqueued on `stream` (a cudaStream_t; NULL = the library's compute stream)
+ * and NOT synchronised.  dA, dB must be 16-byte aligned with even lda, ldb (TMA
+ * global-stride rule); the call aborts otherwise.  `ctas` <= 0 means one
+ * persistent CTA per SM.  Returns the number of kernels launched (1, or 0 for an
+ * empty problem).
+ */
+int phpc_gemm_device(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m, int k, int n,
+                     int ctas, void *stream);
+/* Same contraction through cublasDgemm (alpha = beta = 1) on the same stream. */
+void phpc_gemm_device_cublas(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m, int k,
+                             int n, void *stream);
+/* Run phpc_gemm_device `reps` times back to back and return the mean device
+ * milliseconds per launch (CUDA events on the launching stream). */
+float phpc_gemm_device_timed(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m, int k,
+                             int n, int ctas, int reps, int use_cublas);
+
+/* ---- synthetic inputs (device side) --------------------------------------- */
+/*
+ * Fill the rows x cols window whose top-left element is global (row0, col0) of
+ * an N x N matrix, stored with leading dimension ld at d.
+ *   PHPC_FILL_INDEX   d[r][c] = (double)((row0+r)*N + (col0+c))   (reference
+ *                     src/main.c:85-86, src/iterative.c:30-31)
+ *   PHPC_FILL_SEEDED  uniform in (-1,1) from splitmix64(seed, global flat index):
+ *                     regenerable on any rank, host or device (oracle/fill.py).
+ */
+#define PHPC_FILL_INDEX 0
+#define PHPC_FILL_SEEDED 1
+void phpc_fill_device(double *d, long long ld, long long rows, long long cols, long long row0, long long col0, long long N, int kind,
+                      unsigned long long seed, void *stream);
+/* Host version of the same generators (used by main.out and tests). */
+void phpc_fill_host(double *h, long long ld, long long rows, long long cols, long long row0, long long col0, long long N, int kind,
+                    unsigned long long seed);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

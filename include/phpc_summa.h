@@ -1,0 +1,102 @@
+/*
+ * phpc_summa.h — C-ABI of the SUMMA outer loop (drop-in for the reference's
+ * src/phpc_summa.h:6-8; same names, argument order and meaning), plus the
+ * device-resident additions the B200 build needs.
+ *
+ * Semantics kept from reference src/phpc_summa.c:24-122:
+ *   - grid_comm is a 2-D Cartesian communicator (r x c); N % r == N % c == 0;
+ *   - A, B, C are FULL N x N row-major HOST matrices on every rank; rank (i,j)
+ *     owns rows i*N/r.. of A and C, columns j*N/c.. of B and C; the K dimension is
+ *     cut into lcm(r,c) panels, A panel k is broadcast along the process row by
+ *     column k%c, B panel k along the process column by row k%r (:64-89);
+ *   - C += A*B (the local GEMM accumulates, :93); after return rank 0 holds the
+ *     full C, every other rank its own block at its global offset (:97-110);
+ *   - *compute_time = device seconds of the local GEMMs summed over the steps (:94).
+ * What changed underneath: the panels never touch host memory.  Each rank uploads
+ * its owned blocks once, the k-loop runs on device with ncclBroadcast on per-row /
+ * per-column NCCL communicators, multi-buffered on a communication stream so the
+ * broadcast of step k+1.. overlaps the DMMA GEMM of step k, and the C block comes
+ * back once at the end.  MPI (real or the single-node shim in mpi_shim/) is only
+ * the control plane: bootstrap of the NCCL id, barriers, the final gather.
+ */
+#ifndef _PHPC_SUMMA_H
+#define _PHPC_SUMMA_H
+
+#include <mpi.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* replaces reference src/phpc_summa.c:124-126 */
+void phpc_gemm_summa_cuda(MPI_Comm grid_comm, const double *A, const double *B, double *C, int n, int gpu_count, int grid_width,
+                          int grid_height, int block_width, float *compute_time);
+
+/* replaces reference src/phpc_summa.c:128-130 (same loop, cuBLAS Dgemm as the local GEMM) */
+void phpc_gemm_summa_cublas(MPI_Comm grid_comm, const double *A, const double *B, double *C, int n, int gpu_count, float *compute_time);
+
+/* ======================= additions (not in the reference) ======================= */
+
+#define PHPC_BACKEND_DMMA 0
+#define PHPC_BACKEND_CUBLAS 1
+
+/* One k-step of the schedule as rank (pi, pj) sees it. */
+typedef struct phpc_summa_step {
+  int panel;        /* logical SUMMA panel k of reference :63 (0 .. lcm-1) */
+  int a_root;       /* process column that broadcasts the A chunk (= panel % c, :64) */
+  int b_root;       /* process row that broadcasts the B chunk    (= panel % r, :65) */
+  long long k0;     /* global K offset of the chunk */
+  int width;        /* K extent of the chunk (<= kc) */
+  int own_a, own_b; /* this rank is the root of the A / B broadcast */
+  long long a_off;  /* element offset of the chunk inside this rank's A store (own_a) */
+  long long b_off;  /* element offset of the chunk inside this rank's B store (own_b) */
+} phpc_summa_step;
+
+/* Pure host arithmetic (no GPU, no MPI): the schedule of an N x N SUMMA on an
+ * r x c grid for rank (pi, pj) with K chunks of at most kc columns.  Writes up to
+ * max_steps entries, returns the number of steps (or -1 if N is not divisible by r
+ * and c).  m/n/lda_pad/ldb_pad describe the rank's blocks (may be NULL). */
+int phpc_summa_schedule(int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps, int *m_out, int *n_out);
+
+typedef struct phpc_summa_stats {
+  float total_ms;   /* first broadcast enqueued -> last GEMM complete (device events) */
+  float gemm_ms;    /* sum of the local GEMM kernel durations */
+  float exposed_ms; /* total_ms - gemm_ms: broadcast (and launch) time NOT hidden */
+  int steps;
+  int launches;      /* GEMM kernels launched */
+  int broadcasts;    /* ncclBroadcast calls issued */
+  long long bytes_received; /* NVLink bytes this rank received */
+} phpc_summa_stats;
+
+typedef struct phpc_summa phpc_summa; /* opaque: blocks in HBM + NCCL row/col communicators */
+
+/* Collective over grid_comm.  Binds the rank to a GPU (PHPC_DEVICE, else
+ * LOCAL_RANK, else rank % device_count), builds/caches the NCCL communicators and
+ * allocates the rank's A, B, C blocks and the receive ring in HBM.  kc <= 0 picks
+ * the default (whole panel on a 1x1 grid, 2048 otherwise; env PHPC_KC overrides). */
+phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc);
+void phpc_summa_destroy(phpc_summa *s);
+/* Upload the rank's owned blocks from FULL host matrices (C may be NULL = zero). */
+void phpc_summa_upload(phpc_summa *s, const double *A, const double *B, const double *C);
+/* Generate the owned blocks in HBM (PHPC_FILL_INDEX / PHPC_FILL_SEEDED of
+ * phpc_b200.h, seeds for A and B) and zero C: no host matrices at all. */
+void phpc_summa_fill(phpc_summa *s, int kind, unsigned long long seed_a, unsigned long long seed_b);
+void phpc_summa_zero_c(phpc_summa *s);
+/* The device-resident SUMMA k-loop.  `stream` (cudaStream_t or NULL) is the caller's
+ * stream: the loop starts after work already enqueued on it and the stream waits for
+ * the last GEMM, so events recorded on it bracket the whole step.  Not synchronised
+ * unless stats != NULL (stats need the events to complete). */
+void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *stream, phpc_summa_stats *stats);
+/* D2H of the rank's C block into a FULL N x N host matrix at its global offset, then
+ * (gather != 0) the reference's gather to rank 0 (src/phpc_summa.c:97-110). */
+void phpc_summa_download_c(phpc_summa *s, double *C, int gather);
+/* Copy a rows x cols window of the rank's C block (block-local coordinates) to host. */
+void phpc_summa_read_c_block(phpc_summa *s, double *dst, long long ld, int row0, int col0, int rows, int cols);
+/* Geometry of the rank: dims {r,c}, coords {pi,pj}, block {m,n}. */
+void phpc_summa_geometry(const phpc_summa *s, int dims[2], int coords[2], int block[2]);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
