@@ -154,6 +154,18 @@ extern "C" void phpc_device_memset(void *p, int value, size_t bytes) {
   CUDA_CHECK(cudaMemsetAsync(p, value, bytes, ctx->compute));
   CUDA_CHECK(cudaStreamSynchronize(ctx->compute));
 }
+extern "C" void phpc_copy2d_to_host(double *host, long long ld_host, const double *dev, long long ld_dev, long long rows,
+                                    long long cols) {
+  phpc_cur_ctx();
+  if (rows <= 0 || cols <= 0) return;
+  CUDA_CHECK(cudaMemcpy2D(host, (size_t)ld_host * 8, dev, (size_t)ld_dev * 8, (size_t)cols * 8, (size_t)rows, cudaMemcpyDeviceToHost));
+}
+extern "C" void phpc_copy2d_to_device(double *dev, long long ld_dev, const double *host, long long ld_host, long long rows,
+                                      long long cols) {
+  phpc_cur_ctx();
+  if (rows <= 0 || cols <= 0) return;
+  CUDA_CHECK(cudaMemcpy2D(dev, (size_t)ld_dev * 8, host, (size_t)ld_host * 8, (size_t)cols * 8, (size_t)rows, cudaMemcpyHostToDevice));
+}
 extern "C" void phpc_device_synchronize(void) {
   phpc_cur_ctx();
   CUDA_CHECK(cudaDeviceSynchronize());

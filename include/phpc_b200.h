@@ -39,6 +39,9 @@ void *phpc_host_malloc_pinned(size_t bytes);
 void phpc_host_free_pinned(void *p);
 void phpc_device_memset(void *p, int value, size_t bytes);
 void phpc_device_synchronize(void);
+/* rows x cols doubles between a host matrix (ld_host) and a device matrix (ld_dev); synchronous. */
+void phpc_copy2d_to_host(double *host, long long ld_host, const double *dev, long long ld_dev, long long rows, long long cols);
+void phpc_copy2d_to_device(double *dev, long long ld_dev, const double *host, long long ld_host, long long rows, long long cols);
 
 /* ---- local block GEMM on device pointers --------------------------------- */
 /*

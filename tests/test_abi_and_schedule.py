@@ -1,0 +1,113 @@
+"""CPU-only checks of the boundary: the shared library loads without a GPU, exports every
+symbol include/*.h declares, and the SUMMA schedule follows reference src/phpc_summa.c:36-95."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    names = re.findall(r"\b([a-z_][a-z0-9_]*)\s*\([^;{]*\)\s*;", text, flags=re.S)
+    return [n for n in names if n not in ("defined",)]
+
+
+@pytest.mark.parametrize("header", ["phpc_gemm.cuh", "phpc_summa.h", "phpc_b200.h", "utils.h"])
+def test_library_exports_every_declared_symbol(capi, header):
+    lib = capi.load()
+    names = _declared_functions(header)
+    assert names, f"no declarations parsed from {header}"
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/{header} but not exported"
+
+
+def test_reference_entry_points_present(capi):
+    lib = capi.load()
+    for name in ("phpc_gemm_cuda", "phpc_gemm_cublas", "phpc_gemm_summa_cuda", "phpc_gemm_summa_cublas", "get_cur_time", "log_to_csv"):
+        assert hasattr(lib, name)
+    assert lib.phpc_b200_version() >= 100
+    assert lib.phpc_b200_device_count() >= 0  # never aborts without a GPU
+
+
+def test_log_to_csv_record_is_byte_compatible(capi, tmp_path):
+    """reference src/utils.c:26-27: '%d,%d,%d,%d,%d,%d,%f,%f,%f\\n' with total_threads computed."""
+    lib = capi.load()
+    libc = ctypes.CDLL(None)
+    libc.fopen.restype = ctypes.c_void_p
+    libc.fopen.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    libc.fclose.argtypes = [ctypes.c_void_p]
+    lib.log_to_csv.argtypes = [ctypes.c_void_p] + [ctypes.c_int] * 5 + [ctypes.c_double, ctypes.c_float, ctypes.c_double]
+    path = str(tmp_path / "x.csv")
+    f = libc.fopen(path.encode(), b"w")
+    lib.log_to_csv(f, 2048, 4, 1, 64, 1024, 0.45774, 0.25, 1.5)
+    libc.fclose(f)
+    assert open(path).read() == "2048,4,1,64,1024,65536,0.457740,0.250000,1.500000\n"
+
+
+GRIDS = [(1, 1), (1, 2), (2, 1), (2, 2), (2, 4), (4, 2), (2, 3), (4, 4)]
+
+
+@pytest.mark.parametrize("r,c", GRIDS)
+@pytest.mark.parametrize("kc", [0, 5, 16])
+def test_schedule_matches_reference_ownership(capi, oracle, r, c, kc):
+    lcm = oracle.find_lcm(r, c)
+    N = lcm * 12
+    owner_col, owner_row = oracle.summa_owners(r, c)
+    pk = N // lcm
+    for pi in range(r):
+        for pj in range(c):
+            steps, m, n = capi.summa_schedule(N, r, c, pi, pj, kc)
+            assert (m, n) == (N // r, N // c)
+            # chunks tile K exactly once, in ascending order, never crossing a panel
+            k = 0
+            for s in steps:
+                assert s.k0 == k and s.width > 0
+                assert s.k0 // pk == (s.k0 + s.width - 1) // pk == s.panel
+                k += s.width
+                assert s.a_root == owner_col[s.panel] and s.b_root == owner_row[s.panel]
+                assert s.own_a == int(pj == s.a_root) and s.own_b == int(pi == s.b_root)
+            assert k == N
+            # owned chunks are stored back to back without overlap
+            a_end = 0
+            for s in steps:
+                if s.own_a:
+                    assert s.a_off == a_end
+                    a_end += m * ((s.width + 15) // 16 * 16)
+            owned_b = sorted((s.b_off, s.width) for s in steps if s.own_b)
+            ldn = (n + 15) // 16 * 16
+            end = 0
+            for off, w in owned_b:
+                assert off == end
+                end += w * ldn
+            assert sum(s.width for s in steps if s.own_a) == N // c
+            assert sum(s.width for s in steps if s.own_b) == N // r
+
+
+def test_schedule_rejects_indivisible(capi):
+    with pytest.raises(ValueError):
+        capi.summa_schedule(30, 4, 2, 0, 0)
+
+
+def test_schedule_drives_a_cpu_emulation_to_the_oracle_result(capi, oracle):
+    """Execute the product's schedule with the oracle's block GEMM standing in for the
+    kernel: every rank multiplies exactly the chunks the plan names."""
+    N, r, c, kc = 48, 2, 4, 5
+    A = oracle.fill(N, N, kind=1, seed=oracle.SEED_A)
+    B = oracle.fill(N, N, kind=1, seed=oracle.SEED_B)
+    C = np.zeros((N, N))
+    for pi in range(r):
+        for pj in range(c):
+            steps, m, n = capi.summa_schedule(N, r, c, pi, pj, kc)
+            blk = np.zeros((m, n))
+            for s in steps:
+                a = A[pi * m:(pi + 1) * m, s.k0:s.k0 + s.width]
+                b = B[s.k0:s.k0 + s.width, pj * n:(pj + 1) * n]
+                blk = oracle.gemm_block(a, b, blk)
+            C[pi * m:(pi + 1) * m, pj * n:(pj + 1) * n] = blk
+    assert oracle.rel_frobenius(C, oracle.summa(A, B, r, c)) < 1e-15

@@ -1,0 +1,219 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C-ABI with host buffers
+exactly as the reference's SUMMA loop calls its gemm_t plugin, against the oracle.
+
+Tolerances.  Bit-exact (0 ulp) for the reference's own input A[i]=B[i]=i while every
+partial sum is an integer below 2^53 (N < 1552).  Otherwise relative Frobenius
+error <= 1e-14 against the oracle (which sums in the reference's order; the tensor-core
+kernel sums in a different order, so equality is not expected) and, per element,
+|c - c*| <= 4 * sqrt(k) * 2^-53 * sum_p |a_p||b_p|.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+U = 2.0 ** -53
+
+
+def _check(oracle, c, want, a, b, tol=1e-14):
+    assert oracle.rel_frobenius(c, want) <= tol
+    bound = 4.0 * np.sqrt(max(a.shape[1], 1)) * U * (np.abs(a) @ np.abs(b)) + 1e-300
+    assert np.all(np.abs(c - want) <= bound + 4 * U * np.abs(want))
+
+
+SHAPES = [
+    (1, 1, 1), (8, 4, 8), (64, 64, 64), (128, 16, 128), (128, 128, 128), (129, 17, 131), (100, 37, 53),
+    (300, 215, 170), (257, 511, 255), (512, 1024, 384), (1000, 999, 1001), (130, 2048, 70),
+]
+
+
+@pytest.mark.parametrize("m,k,n", SHAPES)
+def test_gemm_cuda_seeded_vs_oracle(gpu, capi, oracle, m, k, n):
+    a = oracle.fill(m, k, kind=1, seed=101)
+    b = oracle.fill(k, n, kind=1, seed=202)
+    c0 = oracle.fill(m, n, kind=1, seed=303)
+    c = c0.copy()
+    secs = capi.phpc_gemm_cuda(a, b, c)
+    assert secs >= 0.0
+    _check(oracle, c, oracle.gemm_block(a, b, c0), a, b)
+
+
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 200, 512, 1024])
+def test_gemm_cuda_index_fill_bit_exact(gpu, capi, oracle, n):
+    """The reference's input (src/main.c:85-86): exact for any summation order at these sizes."""
+    a = oracle.fill(n, n, kind=0)
+    c = np.zeros((n, n))
+    capi.phpc_gemm_cuda(a, a.copy(), c)
+    assert np.array_equal(c, oracle.index_fill_exact(n))
+
+
+def test_gemm_cuda_interior_pointers_and_leading_dimensions(gpu, capi, oracle):
+    """The SUMMA owner passes interior pointers with ld = N (reference src/phpc_summa.c:72-73,82-83)."""
+    N = 96
+    A = oracle.fill(N, N, kind=1, seed=1)
+    B = oracle.fill(N, N, kind=1, seed=2)
+    C = oracle.fill(N, N, kind=1, seed=3)
+    C0 = C.copy()
+    a, b, c = A[24:72, 32:64], B[32:64, 48:96], C[24:72, 48:96]
+    capi.phpc_gemm_cuda(a, b, c)
+    want = C0.copy()
+    want[24:72, 48:96] = oracle.gemm_block(a.copy(), b.copy(), C0[24:72, 48:96].copy())
+    assert oracle.rel_frobenius(C, want) <= 1e-14
+    mask = np.ones_like(C, dtype=bool)
+    mask[24:72, 48:96] = False
+    assert np.array_equal(C[mask], C0[mask])  # nothing outside the block is touched
+
+
+def test_gemm_cuda_empty_and_degenerate(gpu, capi, oracle):
+    c = np.ones((4, 6))
+    capi.phpc_gemm_cuda(np.zeros((4, 0)), np.zeros((0, 6)), c)  # k = 0: C unchanged
+    assert np.array_equal(c, np.ones((4, 6)))
+    capi.phpc_gemm_cuda(np.zeros((0, 5)), np.zeros((5, 6)), np.zeros((0, 6)))  # m = 0: no-op
+
+
+@pytest.mark.parametrize("tile_width,gw,gh", [(1, 1, 1), (16, 1, 1), (32, 2, 2), (32, 4, 4), (64, 148, 4), (256, 7, 3)])
+def test_launch_parameters_never_change_the_result(gpu, capi, oracle, tile_width, gw, gh):
+    """tile_width / grid_width / grid_height of the CLI and CSV sweeps (tests/*.csv) are accepted."""
+    m, k, n = 260, 100, 390
+    a = oracle.fill(m, k, kind=1, seed=5)
+    b = oracle.fill(k, n, kind=1, seed=6)
+    c = np.zeros((m, n))
+    capi.phpc_gemm_cuda(a, b, c, 1, gw, gh, tile_width)
+    ref = np.zeros((m, n))
+    capi.phpc_gemm_cuda(a, b, ref)
+    assert np.array_equal(c, ref)
+    _check(oracle, c, oracle.gemm_block(a, b), a, b)
+
+
+def test_gemm_cublas_entry_point(gpu, capi, oracle):
+    m, k, n = 200, 150, 100
+    a = oracle.fill(m, k, kind=1, seed=7)
+    b = oracle.fill(k, n, kind=1, seed=8)
+    c0 = oracle.fill(m, n, kind=1, seed=9)
+    c = c0.copy()
+    t = capi.phpc_gemm_cublas(a, b, c)
+    assert t == 0.0  # reference src/phpc_gemm.cu:173
+    _check(oracle, c, oracle.gemm_block(a, b, c0), a, b)
+
+
+@pytest.mark.parametrize("n", [64, 256, 1024])
+def test_summa_single_rank_bit_exact_on_reference_fill(gpu, capi, oracle, n):
+    """BASELINE config 1 (N=1024, 1 rank) through phpc_gemm_summa_cuda, vs iterative.c's result."""
+    comm = capi.cart_create((1, 1))
+    A = oracle.fill(n, n, kind=0)
+    C = np.zeros((n, n))
+    secs = capi.phpc_gemm_summa_cuda(comm, A, A.copy(), C, 1, 1, 1, 32)
+    assert secs > 0.0
+    assert np.array_equal(C, oracle.index_fill_exact(n))
+    if n <= 256:
+        assert np.array_equal(C, oracle.gemm_iterative(A, A))
+
+
+def test_summa_single_rank_matches_golden_and_accumulates(gpu, capi, oracle):
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_outputs.npz"))
+    n = 48
+    comm = capi.cart_create((1, 1))
+    A = oracle.fill(n, n, kind=1, seed=oracle.SEED_A)
+    B = oracle.fill(n, n, kind=1, seed=oracle.SEED_B)
+    C = np.zeros((n, n))
+    capi.phpc_gemm_summa_cuda(comm, A, B, C)
+    assert oracle.rel_frobenius(C, g["summa_N48_P1_F1"]) <= 1e-14
+    first = C.copy()
+    capi.phpc_gemm_summa_cuda(comm, A, B, C)  # C += A*B again (reference main.c runs both passes on one C)
+    assert oracle.rel_frobenius(C, 2 * first) <= 1e-15
+    Cb = np.zeros((n, n))
+    capi.phpc_gemm_summa_cublas(comm, A, B, Cb)
+    assert oracle.rel_frobenius(Cb, g["summa_N48_P1_F1"]) <= 1e-14
+
+
+def test_summa_chunked_k_loop_device_resident(gpu, capi, oracle):
+    """K chunking (the multi-buffered loop) must not change the result beyond rounding."""
+    n = 384
+    comm = capi.cart_create((1, 1))
+    A = oracle.fill(n, n, kind=1, seed=oracle.SEED_A)
+    B = oracle.fill(n, n, kind=1, seed=oracle.SEED_B)
+    want = oracle.gemm_block(A, B)
+    for kc in (0, 37, 128):
+        s = capi.Summa(comm, n, kc)
+        s.fill(capi.FILL_SEEDED)
+        st = s.run(capi.BACKEND_DMMA)
+        assert st.steps == (1 if kc == 0 else -(-n // kc)) and st.launches == st.steps
+        assert oracle.rel_frobenius(s.read_c_block(), want) <= 1e-14
+        s.zero_c()
+        s.run(capi.BACKEND_CUBLAS)
+        assert oracle.rel_frobenius(s.read_c_block(), want) <= 1e-14
+        s.destroy()
+
+
+def _device_gemm(capi, lib, n, kind, scale=1.0, cublas=False):
+    """C = (scale*A) * B for the N x N synthetic matrices, all in HBM; returns device pointer of C."""
+    ld = n
+    bytes_ = n * ld * 8
+    dA, dB, dC = (lib.phpc_device_malloc(bytes_) for _ in range(3))
+    lib.phpc_fill_device(dA, ld, n, n, 0, 0, n, kind, capi.SEED_A, None)
+    lib.phpc_fill_device(dB, ld, n, n, 0, 0, n, kind, capi.SEED_B, None)
+    lib.phpc_device_memset(dC, 0, bytes_)
+    return dA, dB, dC
+
+
+def test_full_size_n16384_properties(gpu, capi, oracle):
+    """BASELINE config 2 (N=16384, one GPU): size-independent properties instead of a CPU GEMM.
+    (a) 256 sampled elements against correctly rounded dot products of regenerated rows/columns;
+    (b) against cuBLAS Dgemm on the same device inputs (rel Frobenius on a 2048x2048 window);
+    (c) linearity: running the GEMM twice into the same C doubles it (C += semantics)."""
+    lib = gpu
+    n = 16384
+    dA, dB, dC = _device_gemm(capi, lib, n, capi.FILL_SEEDED)
+    assert lib.phpc_gemm_device(dA, n, dB, n, dC, n, n, n, n, 0, None) == 1
+    lib.phpc_device_synchronize()
+
+    def window(ptr, r0, c0, rows, cols):
+        return capi.device_window(ptr, n, r0, c0, rows, cols)
+
+    rng = np.random.default_rng(7)
+    rows = rng.integers(0, n, 16)
+    cols = rng.integers(0, n, 16)
+    worst = 0.0
+    for r in rows:
+        crow = window(dC, int(r), 0, 1, n)[0]
+        a_row = oracle.fill(1, n, row0=int(r), col0=0, N=n, kind=1, seed=oracle.SEED_A)[0]
+        for c in cols:
+            b_col = oracle.fill(n, 1, row0=0, col0=int(c), N=n, kind=1, seed=oracle.SEED_B)[:, 0]
+            exact = oracle.dot_exact(a_row, b_col)
+            bound = 4.0 * np.sqrt(n) * U * float(np.abs(a_row) @ np.abs(b_col))
+            assert abs(crow[c] - exact) <= bound
+            worst = max(worst, abs(crow[c] - exact) / bound)
+    # (b) cuBLAS on the same inputs
+    dC2 = lib.phpc_device_malloc(n * n * 8)
+    lib.phpc_device_memset(dC2, 0, n * n * 8)
+    lib.phpc_gemm_device_cublas(dA, n, dB, n, dC2, n, n, n, n, None)
+    lib.phpc_device_synchronize()
+    w1 = window(dC, 4096, 8192, 512, 2048)
+    w2 = window(dC2, 4096, 8192, 512, 2048)
+    assert oracle.rel_frobenius(w1, w2) <= 1e-14
+    # (c) C += : second pass doubles every element exactly (x + x is exact in binary FP)
+    lib.phpc_gemm_device(dA, n, dB, n, dC, n, n, n, n, 0, None)
+    lib.phpc_device_synchronize()
+    w3 = window(dC, 4096, 8192, 512, 2048)
+    assert oracle.rel_frobenius(w3, 2 * w1) <= 1e-15
+    for p in (dA, dB, dC, dC2):
+        lib.phpc_device_free(p)
+    print(f"N=16384 sampled-dot worst error / bound = {worst:.3f}")
+
+
+def test_index_fill_large_n_against_closed_form(gpu, capi, oracle):
+    """N=4096 reference fill: values reach 2^48 * 4096, sums are no longer exact; compare with the
+    int128 closed form (rounded once) under the relative tolerance."""
+    n = 4096
+    comm = capi.cart_create((1, 1))
+    s = capi.Summa(comm, n, 1024)
+    s.fill(capi.FILL_INDEX)
+    s.run()
+    got = s.read_c_block(1000, 3000, 64, 512)
+    want = oracle.index_fill_exact(n, 1000, 3000, 64, 512)
+    assert oracle.rel_frobenius(got, want) <= 1e-14
+    s.destroy()
