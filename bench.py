@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""
+bench.py — SUMMA GEMM TFLOP/s at N=32768 on 1/2/4/8 B200 (BASELINE.json's metric).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 \
+        --master-port 29500 bench.py --gpus 4 --steps 3 --warmup 3
+    python bench.py --impl reference ...      # the reference's own CPU GEMM on the host cores
+
+A "step" is one whole SUMMA  C += A*B  (FP64, N x N, 2*N^3 flop) on the r x c process
+grid (1x1, 1x2, 2x2, 2x4 for 1, 2, 4, 8 GPUs), one process per GPU.  N is fixed as the
+GPU count grows ("scaling": "strong").
+  value  device-resident: every rank's owned A/B blocks already in HBM, timed with CUDA
+         events on the launching stream around K steps, max over ranks.
+  e2e    the reference-facing C-ABI call phpc_gemm_summa_cuda() on FULL N x N HOST
+         matrices: upload of the owned blocks, the k-loop, download of C and the gather
+         to rank 0 are all inside the timed region (wall clock around a synchronous call,
+         bracketed by barriers, max over ranks).
+  roofline  the DMMA GEMM kernel: 2*m*k*n flop per launch / mean launch duration (CUDA
+         events recorded around every launch inside the timed region) against the
+         FP64 peak measured on this pool (profiles/fp64_peak_r01.json).
+  cpu_baseline  the reference's iterative.c (oracle/_ref, compiled unchanged with the
+         reference's flags) on ONE host core at a bounded size.
+torch is plumbing only (process group, events, synchronize); all math goes through
+libphpc_b200.so.  The oracle is touched only by the cpu_baseline / --impl reference legs.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "summa_gemm_tflops"
+UNIT = "TFLOP/s"
+GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+CPU_SAMPLE_N = 1024
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the reference's own iterative.c
+# ----------------------------------------------------------------------------
+def _iterative_binary(opt):
+    path = os.path.join(ROOT, "oracle", "_ref", f"iterative_{opt}.out")
+    return path if os.path.exists(path) else None
+
+
+def run_reference_cpu(n, opt="O0"):
+    """One run of the reference's CPU GEMM; returns (tflops, seconds, kind)."""
+    exe = _iterative_binary(opt)
+    if exe:
+        out = subprocess.run([exe, str(n)], check=True, capture_output=True, text=True).stdout.strip()
+        secs = float(out.split(",")[1])  # reference prints "n,seconds" (src/iterative.c:39)
+        kind = "reference"
+    else:  # /root/reference was absent at build time: time the restatement instead
+        from oracle import oracle
+
+        a = oracle.fill(n, n, kind=0)
+        t0 = time.perf_counter()
+        oracle.gemm_iterative(a, a)
+        secs = time.perf_counter() - t0
+        kind = "port"
+    return 2.0 * n ** 3 / secs / 1e12, secs, kind
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = CPU_SAMPLE_N
+    for _ in range(args.warmup):
+        run_reference_cpu(n)
+    vals, secs = [], []
+    for _ in range(args.steps):
+        v, s, kind = run_reference_cpu(n)
+        vals.append(v)
+        secs.append(s)
+    value = sum(vals) / len(vals)
+    sample = f"iterative.c (gcc -Wall, no -O: reference Makefile:9), N={n}, A[i]=B[i]=i, 1 thread; TFLOP/s = 2N^3/t"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"SUMMA GEMM N={args.n} FP64 (bounded CPU sample N={n})", "N": args.n, "sample_N": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.lines:
+            if not (t0 <= t <= t1 + 0.2):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------
+# product arm
+# ----------------------------------------------------------------------------
+def fp64_peak():
+    """FP64 roofline denominator measured on this pool (tools/fp64_peak.cu -> profiles/)."""
+    path = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+    nominal = 148 * 64 * 2 * 1.965e9 / 1e12  # 64 FP64 FMA/clk/SM at clocks.max.sm
+    try:
+        d = json.load(open(path))
+        dgemm = max(x["burst_tflops"] for x in d["dgemm"])
+        issue = max(max(d["dfma_tflops"].values()), max(d["dmma_tflops"].values()))
+        return max(dgemm, issue), (f"measured FP64 peak on this pool: max(DFMA/DMMA issue-rate microbenchmark {issue:.2f}, cuBLAS Dgemm burst "
+                                   f"{dgemm:.2f}) TFLOP/s, profiles/fp64_peak_r01.json; nominal 148 SM x 64 FMA/clk x 1965 MHz = {nominal:.1f}")
+    except (OSError, KeyError, ValueError):
+        return nominal, f"fallback: nominal FP64 148 SM x 64 FMA/clk x 1965 MHz = {nominal:.1f} TFLOP/s (profiles/fp64_peak_r01.json missing)"
+
+
+def host_matrices(capi, N, dims, coords, pin=True):
+    """FULL N x N host A, B, C as the reference API wants them; only the windows this rank
+    owns are filled and page-locked (the rest of the address range is never touched)."""
+    import numpy as np
+
+    L = capi.load()
+    r, c = dims
+    pi, pj = coords
+    m, n = N // r, N // c
+    A = np.empty((N, N), dtype=np.float64)
+    B = np.empty((N, N), dtype=np.float64)
+    C = np.empty((N, N), dtype=np.float64)
+    dp = capi.c_double_p
+    lcm = r * c // __import__("math").gcd(r, c)
+    pk = N // lcm
+
+    def fill_rows(mat, row0, rows, col0, cols, seed):
+        nthreads = min(8, os.cpu_count() or 1, max(1, rows // 64))
+        per = (rows + nthreads - 1) // nthreads
+
+        def work(t):
+            lo, hi = row0 + t * per, min(row0 + rows, row0 + (t + 1) * per)
+            if lo < hi:
+                ptr = ctypes.cast(mat.ctypes.data + (lo * N + col0) * 8, dp)
+                L.phpc_fill_host(ptr, N, hi - lo, cols, lo, col0, N, capi.FILL_SEEDED, seed)
+
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+
+    regs = []
+    # A: rows of this process row, the K panels this process column owns
+    for k in range(lcm):
+        if k % c == pj:
+            fill_rows(A, pi * m, m, k * pk, pk, capi.SEED_A)
+    # B: the K panels this process row owns, columns of this process column
+    for k in range(lcm):
+        if k % r == pi:
+            fill_rows(B, k * pk, pk, pj * n, n, capi.SEED_B)
+            regs.append((B.ctypes.data + (k * pk * N) * 8, pk * N * 8))
+    regs.append((A.ctypes.data + (pi * m * N) * 8, m * N * 8))
+    C[pi * m:(pi + 1) * m, pj * n:(pj + 1) * n] = 0.0
+    regs.append((C.ctypes.data + (pi * m * N) * 8, m * N * 8))
+    if pin:
+        for ptr, nbytes in regs:
+            L.phpc_host_register(ptr, nbytes)
+    return A, B, C, regs
+
+
+def product_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from hpc_multigpu_matrixmult_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if world not in GRIDS:
+        raise SystemExit("supported GPU counts: 1, 2, 4, 8")
+    L = capi.load()  # raises if the CUDA library is missing: no fallback
+    if not torch.cuda.is_available() or L.phpc_b200_device_count() < 1:
+        raise SystemExit("bench.py needs a B200: no CUDA device visible and there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    L.phpc_b200_set_device(local_rank)
+
+    seg = None
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        box = [None]
+        if rank == 0:
+            seg = f"/dev/shm/phpc_bench_{os.getpid()}_{int(time.time())}"
+            capi.mpi_segment_create(seg, world)
+            box[0] = seg
+        dist.broadcast_object_list(box, src=0)
+        seg = box[0]
+    capi.mpi_init(rank, world, seg)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    N = args.n
+    dims = GRIDS[world]
+    comm = capi.cart_create(dims)
+    flops = 2.0 * N ** 3
+
+    # ---------------- device-resident SUMMA: `value` ----------------
+    s = capi.Summa(comm, N, args.kc)
+    s.fill(capi.FILL_SEEDED)
+    stream = torch.cuda.current_stream()
+    sptr = ctypes.c_void_p(stream.cuda_stream)
+    for _ in range(args.warmup):
+        s.run(capi.BACKEND_DMMA, 0, sptr, stats=False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
+    e0.record(stream)
+    st = None
+    for i in range(args.steps):
+        last = i == args.steps - 1
+        st = s.run(capi.BACKEND_DMMA, 0, sptr, stats=last)  # per-launch events are read on the last step
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    t_end = time.perf_counter()
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    value = flops / (ms_per_step * 1e-3) / 1e12
+
+    launches_per_step = st.launches
+    kernel_ms = st.gemm_ms / max(st.launches, 1)
+    m_blk, n_blk = s.block
+    k_per_launch = N / st.steps
+    kernel_tflops = 2.0 * m_blk * n_blk * k_per_launch / (kernel_ms * 1e-3) / 1e12
+    exposed_frac = max_over_ranks(st.exposed_ms / st.total_ms if st.total_ms > 0 else 0.0)
+    peak, peak_src = fp64_peak()
+    bytes_rx = st.bytes_received
+    steps_per_summa = st.steps
+    kc_used = int(k_per_launch)
+    s.destroy()
+
+    # ---------------- e2e through the reference-facing C-ABI on host matrices ----------------
+    e2e = None
+    if not args.no_e2e:
+        coords = (rank // dims[1], rank % dims[1])
+        A, B, C, regs = host_matrices(capi, N, dims, coords)
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        capi.phpc_gemm_summa_cuda(comm, A, B, C)  # warm-up: allocates the cached device blocks
+        times = []
+        for _ in range(e2e_steps):
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            capi.phpc_gemm_summa_cuda(comm, A, B, C)
+            torch.cuda.synchronize()
+            barrier()
+            times.append(time.perf_counter() - t0)
+        e2e_s = max_over_ranks(sum(times) / len(times))
+        for ptr, _ in regs:
+            L.phpc_host_unregister(ptr)
+        L.phpc_summa_release_cache()
+        e2e = {"value": flops / e2e_s / 1e12, "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * N * N, "d2h_bytes_per_step": 8 * N * N,
+               "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "api": "phpc_gemm_summa_cuda(grid_comm, A, B, C, N, ...) on page-locked full N x N host matrices; owned blocks H2D, C block D2H + gather to rank 0 inside the timed region"}
+
+    # ---------------- CPU baseline beside it (rank 0, single GPU run only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v0, s0, kind = run_reference_cpu(CPU_SAMPLE_N, "O0")
+        cpu = {"value": v0, "unit": UNIT, "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
+               "sample": f"iterative.c N={CPU_SAMPLE_N} (reference fill), 1 thread, reference flags gcc -Wall (no -O): {s0:.3f} s"}
+        if _iterative_binary("O3"):
+            v3, s3, _ = run_reference_cpu(CPU_SAMPLE_N, "O3")
+            cpu["value_O3"] = v3
+            cpu["sample"] += f"; same source with -O3: {s3:.3f} s"
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"SUMMA C+=A*B, N={N}, FP64, splitmix64-seeded uniform(-1,1) A/B generated in HBM, owned blocks device-resident",
+                       "N": N, "process_grid": f"{dims[0]}x{dims[1]}", "k_chunk": kc_used, "summa_steps": steps_per_summa,
+                       "cache": "inputs_larger_than_l2 (operands are GiBs; L2 is 126 MB)", "exposed_broadcast_frac": exposed_frac,
+                       "nvlink_bytes_received_rank0_per_step": bytes_rx},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "tensor", "achieved": kernel_tflops, "peak": peak, "unit": UNIT, "frac": kernel_tflops / peak,
+                         "traffic": None, "kernel": "phpc::dmma_gemm_kernel (FP64 DMMA.8x8x4, TMA + mbarrier pipeline)",
+                         "flops_per_launch": 2.0 * m_blk * n_blk * k_per_launch, "kernel_ms": kernel_ms, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        barrier()
+        if rank == 0 and seg:
+            try:
+                os.unlink(seg)
+            except OSError:
+                pass
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("PHPC_BENCH_N", "32768")))
+    ap.add_argument("--kc", type=int, default=0, help="K chunk (0 = library default)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        product_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -96,6 +96,8 @@ def load():
     L.phpc_host_malloc_pinned.argtypes = [ctypes.c_size_t]
     L.phpc_host_malloc_pinned.restype = ctypes.c_void_p
     L.phpc_host_free_pinned.argtypes = [ctypes.c_void_p]
+    L.phpc_host_register.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    L.phpc_host_unregister.argtypes = [ctypes.c_void_p]
     L.phpc_device_memset.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t]
     L.phpc_copy2d_to_host.argtypes = [c_double_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong]
     L.phpc_copy2d_to_device.argtypes = [ctypes.c_void_p, ctypes.c_longlong, c_double_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong]
@@ -119,6 +121,7 @@ def load():
     L.phpc_summa_fill.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_ulonglong]
     L.phpc_summa_zero_c.argtypes = [ctypes.c_void_p]
     L.phpc_summa_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(SummaStats)]
+    L.phpc_summa_run_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int, ctypes.POINTER(SummaStats)]
     L.phpc_summa_download_c.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int]
     L.phpc_summa_read_c_block.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_longlong] + [ctypes.c_int] * 4
     L.phpc_summa_geometry.argtypes = [ctypes.c_void_p, c_int_p, c_int_p, c_int_p]
@@ -160,9 +163,9 @@ def _dp(a):
 def _ld(a):
     """Leading dimension (elements) of a 2-D row-major float64 view."""
     assert a.dtype == np.float64 and a.ndim == 2
-    assert a.shape[1] <= 1 or a.strides[1] == 8, "rows must be contiguous"
-    if a.shape[0] <= 1:
+    if a.size == 0 or a.shape[0] <= 1:
         return max(a.shape[1], 1)
+    assert a.shape[1] <= 1 or a.strides[1] == 8, "rows must be contiguous"
     assert a.strides[0] % 8 == 0
     return a.strides[0] // 8
 
@@ -279,6 +282,11 @@ class Summa:
     def run(self, backend=BACKEND_DMMA, ctas=0, stream=None, stats=True):
         st = SummaStats() if stats else None
         self.L.phpc_summa_run(self.h, backend, ctas, stream, ctypes.byref(st) if stats else None)
+        return st
+
+    def run_host(self, A, B, C, backend=BACKEND_DMMA, ctas=0, gather=True):
+        st = SummaStats()
+        self.L.phpc_summa_run_host(self.h, backend, ctas, _dp(A), _dp(B), _dp(C), 1 if gather else 0, ctypes.byref(st))
         return st
 
     def download_c(self, C, gather=True):

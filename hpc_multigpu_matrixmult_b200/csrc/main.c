@@ -209,6 +209,7 @@ int main(int argc, char *argv[]) {
     }
   }
 
+  phpc_summa_release_cache();
   phpc_b200_finalize();
   MPI_Finalize();
   return 0;

@@ -149,6 +149,11 @@ extern "C" void *phpc_host_malloc_pinned(size_t bytes) {
 extern "C" void phpc_host_free_pinned(void *p) {
   if (p) CUDA_CHECK(cudaFreeHost(p));
 }
+extern "C" void phpc_host_register(void *p, size_t bytes) {
+  phpc_cur_ctx();
+  CUDA_CHECK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+}
+extern "C" void phpc_host_unregister(void *p) { CUDA_CHECK(cudaHostUnregister(p)); }
 extern "C" void phpc_device_memset(void *p, int value, size_t bytes) {
   DeviceCtx *ctx = phpc_cur_ctx();
   CUDA_CHECK(cudaMemsetAsync(p, value, bytes, ctx->compute));

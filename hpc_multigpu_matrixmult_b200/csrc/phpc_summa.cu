@@ -139,10 +139,12 @@ struct phpc_summa {
   size_t a_elems = 0, b_elems = 0, c_elems = 0;
   int nbuf = 0;
   double *ringA = nullptr, *ringB = nullptr; /* nbuf receive buffers each */
+  double *gather_stage = nullptr;            /* rank 0: two C-block landing buffers for the gather */
   size_t ringA_elems = 0, ringB_elems = 0;
   std::vector<cudaEvent_t> ev_bcast, ev_free; /* per ring slot */
   std::vector<cudaEvent_t> ev_g0, ev_g1;      /* per step: GEMM start / stop */
-  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_user = nullptr;
+  std::vector<cudaEvent_t> ev_up;             /* per step: owned chunks uploaded (host-sourced runs) */
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_user = nullptr, ev_cup = nullptr;
 };
 
 static int pick_device(int rank) {
@@ -199,7 +201,6 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
 
   s->nbuf = env_int("PHPC_NBUF", 3);
   if (s->nbuf < 2) s->nbuf = 2;
-  if (s->nbuf > nsteps) s->nbuf = nsteps;
   if (s->c > 1) {
     s->ringA_elems = (size_t)s->m * s->lda_k;
     CUDA_CHECK(cudaMalloc(&s->ringA, s->ringA_elems * s->nbuf * sizeof(double)));
@@ -216,10 +217,13 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   }
   s->ev_g0.resize(nsteps);
   s->ev_g1.resize(nsteps);
+  s->ev_up.resize(nsteps);
   for (int q = 0; q < nsteps; ++q) {
     CUDA_CHECK(cudaEventCreate(&s->ev_g0[q]));
     CUDA_CHECK(cudaEventCreate(&s->ev_g1[q]));
+    CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_up[q], cudaEventDisableTiming));
   }
+  CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_cup, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreate(&s->ev_begin));
   CUDA_CHECK(cudaEventCreate(&s->ev_end));
   CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_user, cudaEventDisableTiming));
@@ -235,10 +239,13 @@ extern "C" void phpc_summa_destroy(phpc_summa *s) {
   cudaFree(s->dC);
   if (s->ringA) cudaFree(s->ringA);
   if (s->ringB) cudaFree(s->ringB);
+  if (s->gather_stage) cudaFree(s->gather_stage);
   for (cudaEvent_t e : s->ev_bcast) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_free) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_g0) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_g1) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->ev_up) cudaEventDestroy(e);
+  cudaEventDestroy(s->ev_cup);
   cudaEventDestroy(s->ev_begin);
   cudaEventDestroy(s->ev_end);
   cudaEventDestroy(s->ev_user);
@@ -259,23 +266,25 @@ extern "C" void phpc_summa_zero_c(phpc_summa *s) {
   CUDA_CHECK(cudaStreamSynchronize(s->ctx->compute));
 }
 
-/* owned blocks out of FULL N x N host matrices: the windows reference :42-44 point into */
-extern "C" void phpc_summa_upload(phpc_summa *s, const double *A, const double *B, const double *C) {
-  cudaStream_t st = s->ctx->copy;
+/* owned chunks of step q out of FULL N x N host matrices: the windows reference :42-44 point into */
+static void upload_step(phpc_summa *s, int qi, const double *A, const double *B, cudaStream_t st) {
+  const phpc_summa_step &q = s->steps[qi];
   const size_t N = (size_t)s->N;
-  for (const phpc_summa_step &q : s->steps) {
-    if (q.own_a) {
-      const double *src = A + (size_t)s->pi * s->m * N + (size_t)q.k0;
-      const size_t ld = phpc_pad_ld(q.width);
-      CUDA_CHECK(cudaMemcpy2DAsync(s->dA + q.a_off, ld * sizeof(double), src, N * sizeof(double), (size_t)q.width * sizeof(double), s->m,
-                                   cudaMemcpyHostToDevice, st));
-    }
-    if (q.own_b) {
-      const double *src = B + (size_t)q.k0 * N + (size_t)s->pj * s->n;
-      CUDA_CHECK(cudaMemcpy2DAsync(s->dB + q.b_off, s->ldn * sizeof(double), src, N * sizeof(double), (size_t)s->n * sizeof(double),
-                                   q.width, cudaMemcpyHostToDevice, st));
-    }
+  if (q.own_a) {
+    const double *src = A + (size_t)s->pi * s->m * N + (size_t)q.k0;
+    const size_t ld = phpc_pad_ld(q.width);
+    CUDA_CHECK(cudaMemcpy2DAsync(s->dA + q.a_off, ld * sizeof(double), src, N * sizeof(double), (size_t)q.width * sizeof(double), s->m,
+                                 cudaMemcpyHostToDevice, st));
   }
+  if (q.own_b) {
+    const double *src = B + (size_t)q.k0 * N + (size_t)s->pj * s->n;
+    CUDA_CHECK(cudaMemcpy2DAsync(s->dB + q.b_off, s->ldn * sizeof(double), src, N * sizeof(double), (size_t)s->n * sizeof(double), q.width,
+                                 cudaMemcpyHostToDevice, st));
+  }
+}
+
+static void upload_c(phpc_summa *s, const double *C, cudaStream_t st) {
+  const size_t N = (size_t)s->N;
   if (C) {
     const double *src = C + (size_t)s->pi * s->m * N + (size_t)s->pj * s->n;
     CUDA_CHECK(cudaMemcpy2DAsync(s->dC, s->ldn * sizeof(double), src, N * sizeof(double), (size_t)s->n * sizeof(double), s->m,
@@ -283,6 +292,12 @@ extern "C" void phpc_summa_upload(phpc_summa *s, const double *A, const double *
   } else {
     CUDA_CHECK(cudaMemsetAsync(s->dC, 0, s->c_elems * sizeof(double), st));
   }
+}
+
+extern "C" void phpc_summa_upload(phpc_summa *s, const double *A, const double *B, const double *C) {
+  cudaStream_t st = s->ctx->copy;
+  for (int q = 0; q < (int)s->steps.size(); ++q) upload_step(s, q, A, B, st);
+  upload_c(s, C, st);
   CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
@@ -300,10 +315,17 @@ extern "C" void phpc_summa_fill(phpc_summa *s, int kind, unsigned long long seed
 /* ------------------------------------------------------------------------- */
 /* the k-loop                                                                 */
 /* ------------------------------------------------------------------------- */
-extern "C" void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, phpc_summa_stats *stats) {
+/*
+ * hA/hB/hC != NULL: host-sourced run (the reference-facing entry points).  The owned
+ * chunks of step q are uploaded on the copy stream while earlier steps compute, so
+ * the H2D traffic the reference pays in full before every kernel (src/phpc_gemm.cu:
+ * 111-113) hides under the GEMMs; hC (may be NULL = zeros) is uploaded first.
+ */
+static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, phpc_summa_stats *stats, const double *hA,
+                      const double *hB, const double *hC, bool host_src) {
   DeviceCtx *ctx = s->ctx;
   CUDA_CHECK(cudaSetDevice(ctx->device));
-  cudaStream_t comm = ctx->comm, comp = ctx->compute;
+  cudaStream_t comm = ctx->comm, comp = ctx->compute, copy = ctx->copy;
   const int nsteps = (int)s->steps.size();
   const int comm_sms = env_int("PHPC_COMM_SMS", 0); /* SMs left free for NCCL while broadcasts are in flight */
   int launches = 0, broadcasts = 0;
@@ -313,15 +335,29 @@ extern "C" void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *user_
     CUDA_CHECK(cudaEventRecord(s->ev_user, (cudaStream_t)user_stream));
     CUDA_CHECK(cudaStreamWaitEvent(comm, s->ev_user, 0));
     CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_user, 0));
+    CUDA_CHECK(cudaStreamWaitEvent(copy, s->ev_user, 0));
   }
   CUDA_CHECK(cudaEventRecord(s->ev_begin, comp));
   CUDA_CHECK(cudaStreamWaitEvent(comm, s->ev_begin, 0));
+  if (host_src) {
+    CUDA_CHECK(cudaStreamWaitEvent(copy, s->ev_begin, 0));
+    upload_c(s, hC, copy);
+    CUDA_CHECK(cudaEventRecord(s->ev_cup, copy));
+    CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_cup, 0));
+  }
 
   const bool any_comm = (s->r > 1 || s->c > 1);
-  int issued = 0; /* broadcasts are issued up to nbuf-1 steps ahead of the GEMMs */
-  auto issue_bcast = [&](int q) {
+  /* stage-in of step q = upload of the owned chunks (host-sourced) + the two broadcasts */
+  auto stage_in = [&](int q) {
     const phpc_summa_step &st = s->steps[q];
     const int slot = q % s->nbuf;
+    const bool uploaded = host_src && (st.own_a || st.own_b);
+    if (uploaded) {
+      upload_step(s, q, hA, hB, copy);
+      CUDA_CHECK(cudaEventRecord(s->ev_up[q], copy));
+    }
+    if (!any_comm) return;
+    if (uploaded) CUDA_CHECK(cudaStreamWaitEvent(comm, s->ev_up[q], 0));
     if (q >= s->nbuf) CUDA_CHECK(cudaStreamWaitEvent(comm, s->ev_free[slot], 0)); /* GEMM q-nbuf released the slot */
     NCCL_CHECK(ncclGroupStart());
     if (s->c > 1) {
@@ -342,13 +378,15 @@ extern "C" void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *user_
     CUDA_CHECK(cudaEventRecord(s->ev_bcast[slot], comm));
   };
 
+  int issued = 0;
+  stage_in(issued++);
   for (int q = 0; q < nsteps; ++q) {
-    if (any_comm) {
-      while (issued < nsteps && issued < q + s->nbuf) issue_bcast(issued++);
-      CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_bcast[q % s->nbuf], 0));
-    }
     const phpc_summa_step &st = s->steps[q];
     const int slot = q % s->nbuf;
+    if (any_comm)
+      CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_bcast[slot], 0));
+    else if (host_src)
+      CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_up[q], 0));
     const double *a = st.own_a ? s->dA + st.a_off : s->ringA + (size_t)slot * s->ringA_elems;
     const double *b = st.own_b ? s->dB + st.b_off : s->ringB + (size_t)slot * s->ringB_elems;
     const long long lda = phpc_pad_ld(st.width);
@@ -366,6 +404,8 @@ extern "C" void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *user_
     }
     CUDA_CHECK(cudaEventRecord(s->ev_g1[q], comp));
     if (any_comm) CUDA_CHECK(cudaEventRecord(s->ev_free[slot], comp));
+    /* prefetch: the stage-in of the next nbuf-1 steps runs under this GEMM */
+    while (issued < nsteps && issued < q + s->nbuf) stage_in(issued++);
   }
   CUDA_CHECK(cudaEventRecord(s->ev_end, comp));
   if (user_stream) CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)user_stream, s->ev_end, 0));
@@ -373,6 +413,7 @@ extern "C" void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *user_
   if (stats) {
     CUDA_CHECK(cudaEventSynchronize(s->ev_end));
     CUDA_CHECK(cudaStreamSynchronize(comm));
+    CUDA_CHECK(cudaStreamSynchronize(copy));
     float total = 0.f, gemm = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&total, s->ev_begin, s->ev_end));
     for (int q = 0; q < nsteps; ++q) {
@@ -390,6 +431,17 @@ extern "C" void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *user_
   }
 }
 
+extern "C" void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, phpc_summa_stats *stats) {
+  summa_run(s, backend, ctas, user_stream, stats, nullptr, nullptr, nullptr, false);
+}
+
+extern "C" void phpc_summa_run_host(phpc_summa *s, int backend, int ctas, const double *A, const double *B, double *C, int gather,
+                                    phpc_summa_stats *stats) {
+  phpc_summa_stats local;
+  summa_run(s, backend, ctas, nullptr, stats ? stats : &local, A, B, C, true);
+  phpc_summa_download_c(s, C, gather);
+}
+
 /* ------------------------------------------------------------------------- */
 /* results                                                                    */
 /* ------------------------------------------------------------------------- */
@@ -400,37 +452,98 @@ extern "C" void phpc_summa_read_c_block(phpc_summa *s, double *dst, long long ld
                           (size_t)cols * sizeof(double), rows, cudaMemcpyDeviceToHost));
 }
 
+/*
+ * The reference gathers the C blocks with one strided MPI_Send per rank into rank 0's
+ * host matrix (src/phpc_summa.c:97-110).  Here every block first crosses NVLink into a
+ * staging buffer on rank 0's GPU (ncclSend/ncclRecv on the world communicator, two
+ * buffers so the next receive overlaps the previous D2H) and reaches rank 0's host C
+ * through rank 0's own PCIe link; no host-to-host copy at all.  PHPC_GATHER=mpi keeps
+ * the reference's MPI path (and is what runs when the grid has a single rank).
+ */
 extern "C" void phpc_summa_download_c(phpc_summa *s, double *C, int gather) {
   const size_t N = (size_t)s->N;
-  phpc_summa_read_c_block(s, C + (size_t)s->pi * s->m * N + (size_t)s->pj * s->n, (long long)N, 0, 0, s->m, s->n);
-  if (!gather || s->size == 1) return;
-  /* reference src/phpc_summa.c:97-110: strided C blocks travel to rank 0 */
-  MPI_Datatype block_c;
-  MPI_Type_vector(s->m, s->n, s->N, MPI_DOUBLE, &block_c);
-  MPI_Type_commit(&block_c);
-  if (s->rank == 0) {
+  DeviceCtx *ctx = s->ctx;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  const char *mode = getenv("PHPC_GATHER");
+  const bool use_mpi = mode && !strcmp(mode, "mpi");
+  if (!gather || s->size == 1 || use_mpi) {
+    phpc_summa_read_c_block(s, C + (size_t)s->pi * s->m * N + (size_t)s->pj * s->n, (long long)N, 0, 0, s->m, s->n);
+    if (!gather || s->size == 1) return;
+    MPI_Datatype block_c;
+    MPI_Type_vector(s->m, s->n, s->N, MPI_DOUBLE, &block_c);
+    MPI_Type_commit(&block_c);
+    if (s->rank == 0) {
+      for (int i = 1; i < s->size; ++i) {
+        int co[2];
+        MPI_Cart_coords(s->grid_comm, i, 2, co);
+        MPI_Recv(C + N * (size_t)co[0] * s->m + (size_t)co[1] * s->n, 1, block_c, i, 0, s->grid_comm, MPI_STATUS_IGNORE);
+      }
+    } else {
+      MPI_Send(C + N * (size_t)s->pi * s->m + (size_t)s->pj * s->n, 1, block_c, 0, 0, s->grid_comm);
+    }
+    MPI_Type_free(&block_c);
+    return;
+  }
+  cudaStream_t st = ctx->compute;
+  const size_t row_bytes = (size_t)s->n * sizeof(double);
+  /* own block -> own place (every rank keeps its block at its global offset, reference :44) */
+  CUDA_CHECK(cudaMemcpy2DAsync(C + (size_t)s->pi * s->m * N + (size_t)s->pj * s->n, N * sizeof(double), s->dC, s->ldn * sizeof(double),
+                               row_bytes, s->m, cudaMemcpyDeviceToHost, st));
+  if (s->rank != 0) {
+    NCCL_CHECK(ncclSend(s->dC, s->c_elems, ncclDouble, 0, g_nccl.world, st));
+  } else {
+    if (!s->gather_stage) CUDA_CHECK(cudaMalloc(&s->gather_stage, 2 * s->c_elems * sizeof(double)));
+    cudaEvent_t drained[2];
+    for (int b = 0; b < 2; ++b) CUDA_CHECK(cudaEventCreateWithFlags(&drained[b], cudaEventDisableTiming));
     for (int i = 1; i < s->size; ++i) {
       int co[2];
       MPI_Cart_coords(s->grid_comm, i, 2, co);
-      MPI_Recv(C + N * (size_t)co[0] * s->m + (size_t)co[1] * s->n, 1, block_c, i, 0, s->grid_comm, MPI_STATUS_IGNORE);
+      const int b = i & 1;
+      double *stage = s->gather_stage + (size_t)b * s->c_elems;
+      if (i > 2) CUDA_CHECK(cudaStreamWaitEvent(st, drained[b], 0));
+      NCCL_CHECK(ncclRecv(stage, s->c_elems, ncclDouble, i, g_nccl.world, st));
+      CUDA_CHECK(cudaEventRecord(s->ev_user, st));
+      CUDA_CHECK(cudaStreamWaitEvent(ctx->copy, s->ev_user, 0));
+      CUDA_CHECK(cudaMemcpy2DAsync(C + N * (size_t)co[0] * s->m + (size_t)co[1] * s->n, N * sizeof(double), stage,
+                                   s->ldn * sizeof(double), row_bytes, s->m, cudaMemcpyDeviceToHost, ctx->copy));
+      CUDA_CHECK(cudaEventRecord(drained[b], ctx->copy));
     }
-  } else {
-    MPI_Send(C + N * (size_t)s->pi * s->m + (size_t)s->pj * s->n, 1, block_c, 0, 0, s->grid_comm);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->copy));
+    for (int b = 0; b < 2; ++b) CUDA_CHECK(cudaEventDestroy(drained[b]));
   }
-  MPI_Type_free(&block_c);
+  CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
 /* ------------------------------------------------------------------------- */
 /* the reference's entry points                                               */
 /* ------------------------------------------------------------------------- */
+/* The device blocks and communicators of the last host-pointer call are kept: the
+ * reference's main.c calls the CUDA pass and the cuBLAS pass back to back on the same
+ * grid and size (src/main.c:94,106), and a bench loop calls it repeatedly. */
+static phpc_summa *g_host_plan = nullptr;
+
+extern "C" void phpc_summa_release_cache(void) {
+  if (g_host_plan) phpc_summa_destroy(g_host_plan);
+  g_host_plan = nullptr;
+}
+
 static void summa_host(MPI_Comm grid_comm, const double *A, const double *B, double *C, int n, int backend, int ctas, float *seconds) {
-  phpc_summa *s = phpc_summa_create(grid_comm, n, 0);
-  phpc_summa_upload(s, A, B, C);
+  int dims[2], periods[2], coords[2], size;
+  MPI_Comm_size(grid_comm, &size);
+  MPI_Cart_get(grid_comm, 2, dims, periods, coords);
+  phpc_summa *s = g_host_plan;
+  if (s && !(s->grid_comm == grid_comm && s->N == n && s->size == size && s->r == dims[0] && s->c == dims[1] && s->pi == coords[0] &&
+             s->pj == coords[1])) {
+    phpc_summa_release_cache();
+    s = nullptr;
+  }
+  if (!s) {
+    /* K chunks of 2048 columns even on one GPU: the uploads pipeline under the GEMMs */
+    s = g_host_plan = phpc_summa_create(grid_comm, n, env_int("PHPC_KC", 2048));
+  }
   phpc_summa_stats stats;
-  phpc_summa_run(s, backend, ctas, nullptr, &stats);
-  phpc_summa_download_c(s, C, 1);
+  phpc_summa_run_host(s, backend, ctas, A, B, C, 1, &stats);
   if (seconds) *seconds = stats.gemm_ms / 1000.f;
-  phpc_summa_destroy(s);
 }
 
 extern "C" void phpc_gemm_summa_cuda(MPI_Comm grid_comm, const double *A, const double *B, double *C, int n, int gpu_count, int grid_width,

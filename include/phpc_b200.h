@@ -37,6 +37,9 @@ void *phpc_device_malloc(size_t bytes);
 void phpc_device_free(void *p);
 void *phpc_host_malloc_pinned(size_t bytes);
 void phpc_host_free_pinned(void *p);
+/* Page-lock / unlock a caller-owned host range so copies from it are asynchronous DMA. */
+void phpc_host_register(void *p, size_t bytes);
+void phpc_host_unregister(void *p);
 void phpc_device_memset(void *p, int value, size_t bytes);
 void phpc_device_synchronize(void);
 /* rows x cols doubles between a host matrix (ld_host) and a device matrix (ld_dev); synchronous. */

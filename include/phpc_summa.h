@@ -87,6 +87,13 @@ void phpc_summa_zero_c(phpc_summa *s);
  * the last GEMM, so events recorded on it bracket the whole step.  Not synchronised
  * unless stats != NULL (stats need the events to complete). */
 void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *stream, phpc_summa_stats *stats);
+/* Host-sourced run (what phpc_gemm_summa_cuda does): C += A*B on FULL N x N host matrices,
+ * owned chunks uploaded on a copy stream while earlier chunks compute, C block downloaded
+ * (and gathered to rank 0 when gather != 0) at the end.  Synchronous. */
+void phpc_summa_run_host(phpc_summa *s, int backend, int ctas, const double *A, const double *B, double *C, int gather,
+                         phpc_summa_stats *stats);
+/* Drop the device blocks cached by phpc_gemm_summa_cuda / phpc_gemm_summa_cublas. */
+void phpc_summa_release_cache(void);
 /* D2H of the rank's C block into a FULL N x N host matrix at its global offset, then
  * (gather != 0) the reference's gather to rank 0 (src/phpc_summa.c:97-110). */
 void phpc_summa_download_c(phpc_summa *s, double *C, int gather);

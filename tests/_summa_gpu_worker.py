@@ -1,0 +1,49 @@
+"""Worker of tests/test_multigpu.py, one process per GPU under bin/mpirun:
+    mpirun -n P python tests/_summa_gpu_worker.py <RxC> <N> <fill> <out.npy> [kc]
+Calls the reference-facing C-ABI phpc_gemm_summa_cuda on full host matrices (what the
+reference's main.c does, src/main.c:94) and, with kc given, the device-resident k-loop."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from hpc_multigpu_matrixmult_b200 import capi  # noqa: E402
+
+
+def main():
+    r, c = (int(x) for x in sys.argv[1].split("x"))
+    N, fill, out = int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+    kc = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+    L = capi.load()
+    M = capi.mpi()
+    M.MPI_Init(None, None)
+    rank = int(os.environ.get("PHPC_MPI_RANK", "0"))
+    comm = capi.cart_create((r, c))
+    A = np.empty((N, N))
+    B = np.empty((N, N))
+    L.phpc_fill_host(capi._dp(A), N, N, N, 0, 0, N, fill, capi.SEED_A)
+    L.phpc_fill_host(capi._dp(B), N, N, N, 0, 0, N, fill, capi.SEED_B)
+    C = np.zeros((N, N))
+    secs = capi.phpc_gemm_summa_cuda(comm, A, B, C)
+    assert secs > 0
+    Cb = np.zeros((N, N))
+    capi.phpc_gemm_summa_cublas(comm, A, B, Cb)
+    # device-resident loop with its own chunking and on-device generation of the blocks
+    s = capi.Summa(comm, N, kc)
+    s.fill(fill)
+    st = s.run()
+    Cd = np.zeros((N, N))
+    s.download_c(Cd, gather=True)
+    s.destroy()
+    if rank == 0:
+        np.save(out, np.stack([C, Cb, Cd]))
+        print(f"steps={st.steps} launches={st.launches} bcasts={st.broadcasts} rx={st.bytes_received} "
+              f"total_ms={st.total_ms:.3f} gemm_ms={st.gemm_ms:.3f} exposed_ms={st.exposed_ms:.3f}")
+    L.phpc_summa_release_cache()
+    M.MPI_Finalize()
+
+
+if __name__ == "__main__":
+    main()

@@ -217,3 +217,24 @@ def test_index_fill_large_n_against_closed_form(gpu, capi, oracle):
     want = oracle.index_fill_exact(n, 1000, 3000, 64, 512)
     assert oracle.rel_frobenius(got, want) <= 1e-14
     s.destroy()
+
+
+def test_main_out_cli_single_rank(gpu, tmp_path):
+    """`main.out <matrix_size> <tile_width> <grid_width> <grid_height> <test_name>` (reference
+    src/main.c:28), file name of :75 and the 9-column record of src/utils.c:26-27."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    (tmp_path / "csv").mkdir()
+    for mode in ("host", "device"):
+        env = dict(os.environ, PHPC_VERIFY="1", PHPC_MODE=mode)
+        res = subprocess.run([os.path.join(root, "bin", "main.out"), "1024", "32", "1", "1", "testA"], capture_output=True, text=True,
+                             timeout=300, cwd=tmp_path, env=env)
+        assert res.returncode == 0, res.stdout + res.stderr
+        rec = open(tmp_path / "csv" / "testA_N1024_T1_G1_TW32_GW1_GH1.csv").read().strip().split(",")
+        assert rec[:6] == ["1024", "1", "1", "1", "1024", "1024"] and len(rec) == 9
+        assert float(rec[6]) > 0 and float(rec[7]) > 0 and float(rec[8]) > 0
+    res = subprocess.run([os.path.join(root, "bin", "main.out"), "64", "32", "1", "1", "nodir"], capture_output=True, text=True,
+                         timeout=120, cwd=tmp_path / "csv")
+    assert res.returncode != 0 and "Could not create CSV file" in res.stderr  # csv/ must pre-exist (reference :77-80)

@@ -1,0 +1,85 @@
+"""SUMMA on several GPUs (NCCL row/column broadcasts over NVLink) against the oracle's
+restatement of reference src/phpc_summa.c.  Needs >= 2 GPUs: run with `gpurun --gpus N`."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _need(gpu, n):
+    have = gpu.phpc_b200_device_count()
+    if have < n:
+        pytest.skip(f"needs {n} GPUs, {have} visible")
+
+
+def _run(grid, N, fill, tmp_path, kc=0, env=None):
+    r, c = grid
+    out = str(tmp_path / f"c_{r}x{c}_{N}_{fill}.npy")
+    cmd = [os.path.join(ROOT, "bin", "mpirun"), "-n", str(r * c), sys.executable, os.path.join(ROOT, "tests", "_summa_gpu_worker.py"),
+           f"{r}x{c}", str(N), str(fill), out, str(kc)]
+    e = dict(os.environ)
+    e.update(env or {})
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=e)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    return np.load(out), res.stdout
+
+
+GRID_CASES = [((1, 2), 2), ((2, 1), 2), ((2, 2), 4), ((2, 4), 8), ((4, 2), 8)]
+
+
+@pytest.mark.parametrize("grid,ngpu", GRID_CASES)
+def test_summa_matches_reference_summa_seeded(gpu, oracle, tmp_path, grid, ngpu):
+    _need(gpu, ngpu)
+    N = 480  # not a multiple of the 128 tile on any grid: edge tiles everywhere
+    Cs, log = _run(grid, N, 1, tmp_path, kc=50)
+    A = oracle.fill(N, N, kind=1, seed=oracle.SEED_A)
+    B = oracle.fill(N, N, kind=1, seed=oracle.SEED_B)
+    want = oracle.summa(A, B, *grid)
+    for name, C in zip(("host-entry dmma", "host-entry cublas", "device-resident"), Cs):
+        assert oracle.rel_frobenius(C, want) <= 1e-14, name
+    assert "bcasts=" in log
+
+
+@pytest.mark.parametrize("grid,ngpu", GRID_CASES)
+def test_summa_bit_exact_on_reference_fill(gpu, oracle, tmp_path, grid, ngpu):
+    """A[i]=B[i]=i at N=1024 (BASELINE config 1 input): exact integers, any grid, any order."""
+    _need(gpu, ngpu)
+    N = 1024
+    Cs, _ = _run(grid, N, 0, tmp_path, kc=96)
+    exact = oracle.index_fill_exact(N)
+    for C in Cs:
+        assert np.array_equal(C, exact)
+
+
+def test_golden_reference_summa_fixture(gpu, oracle, tmp_path):
+    """The committed outputs of the reference's own SUMMA (4 ranks -> 2x2, N=48)."""
+    _need(gpu, 4)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reference_outputs.npz"))
+    Cs, _ = _run((2, 2), 48, 1, tmp_path)
+    for C in Cs:
+        assert oracle.rel_frobenius(C, g["summa_N48_P4_F1"]) <= 1e-14
+
+
+def test_mpi_gather_path_equals_nvlink_gather(gpu, oracle, tmp_path):
+    _need(gpu, 2)
+    a, _ = _run((1, 2), 256, 1, tmp_path)
+    b, _ = _run((1, 2), 256, 1, tmp_path, env={"PHPC_GATHER": "mpi"})
+    assert np.array_equal(a, b)
+
+
+def test_main_out_cli_multi_rank(gpu, tmp_path):
+    """The drop-in driver under the reference's command line, self-verifying (PHPC_VERIFY)."""
+    _need(gpu, 2)
+    (tmp_path / "csv").mkdir()
+    for mode in ("host", "device"):
+        env = dict(os.environ, PHPC_VERIFY="1", PHPC_MODE=mode)
+        res = subprocess.run([os.path.join(ROOT, "bin", "mpirun"), "--oversubscribe", "-n", "2", os.path.join(ROOT, "bin", "main.out"),
+                              "1024", "32", "1", "1", "testA"], capture_output=True, text=True, timeout=300, cwd=tmp_path, env=env)
+        assert res.returncode == 0, res.stdout + res.stderr
+        line = open(tmp_path / "csv" / "testA_N1024_T2_G1_TW32_GW1_GH1.csv").read().strip().split(",")
+        assert line[:6] == ["1024", "2", "1", "1", "1024", "1024"] and len(line) == 9
