@@ -122,6 +122,8 @@ def load():
     L.phpc_summa_zero_c.argtypes = [ctypes.c_void_p]
     L.phpc_summa_run.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(SummaStats)]
     L.phpc_summa_run_host.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int, ctypes.POINTER(SummaStats)]
+    L.phpc_summa_timeline.argtypes = [ctypes.c_void_p, c_float_p, c_float_p, ctypes.c_int]
+    L.phpc_summa_timeline.restype = ctypes.c_int
     L.phpc_summa_download_c.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_int]
     L.phpc_summa_read_c_block.argtypes = [ctypes.c_void_p, c_double_p, ctypes.c_longlong] + [ctypes.c_int] * 4
     L.phpc_summa_geometry.argtypes = [ctypes.c_void_p, c_int_p, c_int_p, c_int_p]
@@ -283,6 +285,12 @@ class Summa:
         st = SummaStats() if stats else None
         self.L.phpc_summa_run(self.h, backend, ctas, stream, ctypes.byref(st) if stats else None)
         return st
+
+    def timeline(self):
+        n = 4096
+        a, b = (ctypes.c_float * n)(), (ctypes.c_float * n)()
+        k = self.L.phpc_summa_timeline(self.h, a, b, n)
+        return [(a[i], b[i]) for i in range(k)]
 
     def run_host(self, A, B, C, backend=BACKEND_DMMA, ctas=0, gather=True):
         st = SummaStats()

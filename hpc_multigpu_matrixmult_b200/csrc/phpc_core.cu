@@ -60,6 +60,7 @@ DeviceCtx *phpc_ctx(int device) {
   CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->compute, cudaStreamNonBlocking, lo));
   CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->comm, cudaStreamNonBlocking, hi));
+  CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->comm2, cudaStreamNonBlocking, hi));
   CUDA_CHECK(cudaStreamCreateWithPriority(&ctx->copy, cudaStreamNonBlocking, lo));
   CUBLAS_CHECK(cublasCreate(&ctx->blas));
   CUDA_CHECK(cudaMalloc(&ctx->sched, 64));
@@ -122,6 +123,7 @@ extern "C" void phpc_b200_finalize(void) {
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->compute);
     cudaStreamDestroy(ctx->comm);
+    cudaStreamDestroy(ctx->comm2);
     cudaStreamDestroy(ctx->copy);
     *ctx = DeviceCtx();
   }

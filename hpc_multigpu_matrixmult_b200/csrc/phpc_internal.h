@@ -44,7 +44,8 @@ struct DeviceCtx {
   int device = -1;
   int sm_count = 0;
   cudaStream_t compute = nullptr; /* GEMM launches */
-  cudaStream_t comm = nullptr;    /* NCCL broadcasts (high priority) */
+  cudaStream_t comm = nullptr;    /* NCCL broadcasts / A-panel pulls (high priority) */
+  cudaStream_t comm2 = nullptr;   /* B-panel pulls (high priority) */
   cudaStream_t copy = nullptr;    /* H2D / D2H staging */
   cublasHandle_t blas = nullptr;
   unsigned int *sched = nullptr; /* tile-scheduler words, self-resetting */

@@ -140,6 +140,12 @@ struct phpc_summa {
   int nbuf = 0;
   double *ringA = nullptr, *ringB = nullptr; /* nbuf receive buffers each */
   double *gather_stage = nullptr;            /* rank 0: two C-block landing buffers for the gather */
+  /* panel transport: 0 = ncclBroadcast on row/column communicators, 1 = copy-engine pull from the
+   * owner's store through CUDA IPC peer mappings (no SMs, no rendezvous) */
+  int transport = 0;
+  std::vector<double *> peerA, peerB;        /* peerA[pj'] = dA of rank (pi, pj'); peerB[pi'] = dB of rank (pi', pj) */
+  std::vector<long long> root_a_off, root_b_off; /* per step: chunk offset inside its ROOT's store */
+  std::vector<cudaEvent_t> ev_bcast2;        /* per ring slot: B pull done (pull transport) */
   size_t ringA_elems = 0, ringB_elems = 0;
   std::vector<cudaEvent_t> ev_bcast, ev_free; /* per ring slot */
   std::vector<cudaEvent_t> ev_g0, ev_g1;      /* per step: GEMM start / stop */
@@ -199,6 +205,45 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   CUDA_CHECK(cudaMalloc(&s->dC, s->c_elems * sizeof(double)));
   CUDA_CHECK(cudaMemset(s->dC, 0, s->c_elems * sizeof(double)));
 
+  /* where every chunk lives on the rank that owns it (needed to pull it) */
+  s->root_a_off.assign(nsteps, -1);
+  s->root_b_off.assign(nsteps, -1);
+  {
+    std::vector<phpc_summa_step> tmp(nsteps);
+    for (int pj2 = 0; pj2 < s->c; ++pj2) {
+      phpc_summa_schedule(n, s->r, s->c, s->pi, pj2, kc, tmp.data(), nsteps, nullptr, nullptr);
+      for (int q = 0; q < nsteps; ++q)
+        if (tmp[q].own_a) s->root_a_off[q] = tmp[q].a_off;
+    }
+    for (int pi2 = 0; pi2 < s->r; ++pi2) {
+      phpc_summa_schedule(n, s->r, s->c, pi2, s->pj, kc, tmp.data(), nsteps, nullptr, nullptr);
+      for (int q = 0; q < nsteps; ++q)
+        if (tmp[q].own_b) s->root_b_off[q] = tmp[q].b_off;
+    }
+  }
+  {
+    const char *t = getenv("PHPC_PANEL");
+    s->transport = (s->size > 1 && !(t && !strcmp(t, "nccl"))) ? 1 : 0;
+  }
+  if (s->size > 1 && s->transport == 1) {
+    /* exchange CUDA IPC handles of the A and B stores over the control plane */
+    struct Handles {
+      cudaIpcMemHandle_t a, b;
+    };
+    std::vector<Handles> all(s->size);
+    CUDA_CHECK(cudaIpcGetMemHandle(&all[s->rank].a, s->dA));
+    CUDA_CHECK(cudaIpcGetMemHandle(&all[s->rank].b, s->dB));
+    for (int root = 0; root < s->size; ++root) MPI_Bcast(&all[root], (int)sizeof(Handles), MPI_BYTE, root, grid_comm);
+    s->peerA.assign(s->c, nullptr);
+    s->peerB.assign(s->r, nullptr);
+    for (int pj2 = 0; pj2 < s->c; ++pj2)
+      if (pj2 != s->pj)
+        CUDA_CHECK(cudaIpcOpenMemHandle((void **)&s->peerA[pj2], all[s->pi * s->c + pj2].a, cudaIpcMemLazyEnablePeerAccess));
+    for (int pi2 = 0; pi2 < s->r; ++pi2)
+      if (pi2 != s->pi)
+        CUDA_CHECK(cudaIpcOpenMemHandle((void **)&s->peerB[pi2], all[pi2 * s->c + s->pj].b, cudaIpcMemLazyEnablePeerAccess));
+  }
+
   s->nbuf = env_int("PHPC_NBUF", 3);
   if (s->nbuf < 2) s->nbuf = 2;
   if (s->c > 1) {
@@ -210,9 +255,11 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
     CUDA_CHECK(cudaMalloc(&s->ringB, s->ringB_elems * s->nbuf * sizeof(double)));
   }
   s->ev_bcast.resize(s->nbuf);
+  s->ev_bcast2.resize(s->nbuf);
   s->ev_free.resize(s->nbuf);
   for (int b = 0; b < s->nbuf; ++b) {
     CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_bcast[b], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_bcast2[b], cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_free[b], cudaEventDisableTiming));
   }
   s->ev_g0.resize(nsteps);
@@ -234,6 +281,14 @@ extern "C" void phpc_summa_destroy(phpc_summa *s) {
   if (!s) return;
   CUDA_CHECK(cudaSetDevice(s->ctx->device));
   CUDA_CHECK(cudaDeviceSynchronize());
+  if (s->size > 1 && s->transport == 1) {
+    MPI_Barrier(s->grid_comm); /* nobody is still pulling from the stores freed below */
+    for (double *p : s->peerA)
+      if (p) cudaIpcCloseMemHandle(p);
+    for (double *p : s->peerB)
+      if (p) cudaIpcCloseMemHandle(p);
+  }
+  for (cudaEvent_t e : s->ev_bcast2) cudaEventDestroy(e);
   cudaFree(s->dA);
   cudaFree(s->dB);
   cudaFree(s->dC);
@@ -299,6 +354,7 @@ extern "C" void phpc_summa_upload(phpc_summa *s, const double *A, const double *
   for (int q = 0; q < (int)s->steps.size(); ++q) upload_step(s, q, A, B, st);
   upload_c(s, C, st);
   CUDA_CHECK(cudaStreamSynchronize(st));
+  if (s->size > 1) MPI_Barrier(s->grid_comm); /* every store is valid before anyone pulls from it */
 }
 
 extern "C" void phpc_summa_fill(phpc_summa *s, int kind, unsigned long long seed_a, unsigned long long seed_b) {
@@ -347,10 +403,43 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
   }
 
   const bool any_comm = (s->r > 1 || s->c > 1);
-  /* stage-in of step q = upload of the owned chunks (host-sourced) + the two broadcasts */
+  const bool pull = any_comm && s->transport == 1;
+  cudaStream_t comm2 = ctx->comm2;
+  if (pull) {
+    CUDA_CHECK(cudaStreamWaitEvent(comm2, s->ev_begin, 0));
+    if (host_src) {
+      /* peers pull straight from this rank's store: make all of it valid, everywhere, first */
+      for (int q = 0; q < nsteps; ++q) upload_step(s, q, hA, hB, copy);
+      CUDA_CHECK(cudaStreamSynchronize(copy));
+      MPI_Barrier(s->grid_comm);
+    }
+  }
+  /* stage-in of step q = upload of the owned chunks (host-sourced) + the panel transfers */
   auto stage_in = [&](int q) {
     const phpc_summa_step &st = s->steps[q];
     const int slot = q % s->nbuf;
+    if (pull) {
+      /* copy-engine pull of the chunks this rank does not own, from the owner's HBM over NVLink */
+      if (s->c > 1 && !st.own_a) {
+        const size_t count = (size_t)s->m * phpc_pad_ld(st.width);
+        if (q >= s->nbuf) CUDA_CHECK(cudaStreamWaitEvent(comm, s->ev_free[slot], 0));
+        CUDA_CHECK(cudaMemcpyAsync(s->ringA + (size_t)slot * s->ringA_elems, s->peerA[st.a_root] + s->root_a_off[q], count * 8,
+                                   cudaMemcpyDeviceToDevice, comm));
+        ++broadcasts;
+        bytes_rx += (long long)count * 8;
+      }
+      CUDA_CHECK(cudaEventRecord(s->ev_bcast[slot], comm));
+      if (s->r > 1 && !st.own_b) {
+        const size_t count = (size_t)st.width * s->ldn;
+        if (q >= s->nbuf) CUDA_CHECK(cudaStreamWaitEvent(comm2, s->ev_free[slot], 0));
+        CUDA_CHECK(cudaMemcpyAsync(s->ringB + (size_t)slot * s->ringB_elems, s->peerB[st.b_root] + s->root_b_off[q], count * 8,
+                                   cudaMemcpyDeviceToDevice, comm2));
+        ++broadcasts;
+        bytes_rx += (long long)count * 8;
+      }
+      CUDA_CHECK(cudaEventRecord(s->ev_bcast2[slot], comm2));
+      return;
+    }
     const bool uploaded = host_src && (st.own_a || st.own_b);
     if (uploaded) {
       upload_step(s, q, hA, hB, copy);
@@ -383,10 +472,12 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
   for (int q = 0; q < nsteps; ++q) {
     const phpc_summa_step &st = s->steps[q];
     const int slot = q % s->nbuf;
-    if (any_comm)
+    if (any_comm) {
       CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_bcast[slot], 0));
-    else if (host_src)
+      if (pull) CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_bcast2[slot], 0));
+    } else if (host_src) {
       CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_up[q], 0));
+    }
     const double *a = st.own_a ? s->dA + st.a_off : s->ringA + (size_t)slot * s->ringA_elems;
     const double *b = st.own_b ? s->dB + st.b_off : s->ringB + (size_t)slot * s->ringB_elems;
     const long long lda = phpc_pad_ld(st.width);
@@ -396,7 +487,7 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
       ++launches;
     } else {
       int use = ctas;
-      if (any_comm && comm_sms > 0 && q + 1 < nsteps) {
+      if (any_comm && !pull && comm_sms > 0 && q + 1 < nsteps) {
         const int base = (ctas <= 1 || ctas > ctx->sm_count) ? ctx->sm_count : ctas;
         use = base - comm_sms > 1 ? base - comm_sms : 2;
       }
@@ -413,6 +504,7 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
   if (stats) {
     CUDA_CHECK(cudaEventSynchronize(s->ev_end));
     CUDA_CHECK(cudaStreamSynchronize(comm));
+    CUDA_CHECK(cudaStreamSynchronize(comm2));
     CUDA_CHECK(cudaStreamSynchronize(copy));
     float total = 0.f, gemm = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&total, s->ev_begin, s->ev_end));
@@ -431,6 +523,18 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
   }
 }
 
+/* per-step GEMM start offsets (from the run's begin event) and durations of the LAST run, ms */
+extern "C" int phpc_summa_timeline(phpc_summa *s, float *start_ms, float *dur_ms, int max_steps) {
+  CUDA_CHECK(cudaSetDevice(s->ctx->device));
+  CUDA_CHECK(cudaEventSynchronize(s->ev_end));
+  const int n = (int)s->steps.size() < max_steps ? (int)s->steps.size() : max_steps;
+  for (int q = 0; q < n; ++q) {
+    CUDA_CHECK(cudaEventElapsedTime(&start_ms[q], s->ev_begin, s->ev_g0[q]));
+    CUDA_CHECK(cudaEventElapsedTime(&dur_ms[q], s->ev_g0[q], s->ev_g1[q]));
+  }
+  return n;
+}
+
 extern "C" void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, phpc_summa_stats *stats) {
   summa_run(s, backend, ctas, user_stream, stats, nullptr, nullptr, nullptr, false);
 }
@@ -440,6 +544,7 @@ extern "C" void phpc_summa_run_host(phpc_summa *s, int backend, int ctas, const 
   phpc_summa_stats local;
   summa_run(s, backend, ctas, nullptr, stats ? stats : &local, A, B, C, true);
   phpc_summa_download_c(s, C, gather);
+  if (s->size > 1 && s->transport == 1) MPI_Barrier(s->grid_comm); /* peers are done pulling before the next upload */
 }
 
 /* ------------------------------------------------------------------------- */

@@ -73,7 +73,12 @@ typedef struct phpc_summa phpc_summa; /* opaque: blocks in HBM + NCCL row/col co
 /* Collective over grid_comm.  Binds the rank to a GPU (PHPC_DEVICE, else
  * LOCAL_RANK, else rank % device_count), builds/caches the NCCL communicators and
  * allocates the rank's A, B, C blocks and the receive ring in HBM.  kc <= 0 picks
- * the default (whole panel on a 1x1 grid, 2048 otherwise; env PHPC_KC overrides). */
+ * the default (whole panel on a 1x1 grid, 2048 otherwise; env PHPC_KC overrides).
+ * Panel transport (env PHPC_PANEL): "nccl" = ncclBroadcast on the row / column
+ * communicators; "pull" (default) = each rank copies the chunks it does not own
+ * straight out of the owner's HBM with the copy engines over NVLink (CUDA IPC peer
+ * mappings): same data movement as the broadcast, but no SMs and no rendezvous.
+ * create / destroy / upload / fill / run_host are collective over grid_comm. */
 phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc);
 void phpc_summa_destroy(phpc_summa *s);
 /* Upload the rank's owned blocks from FULL host matrices (C may be NULL = zero). */
@@ -87,6 +92,9 @@ void phpc_summa_zero_c(phpc_summa *s);
  * the last GEMM, so events recorded on it bracket the whole step.  Not synchronised
  * unless stats != NULL (stats need the events to complete). */
 void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *stream, phpc_summa_stats *stats);
+/* Per-step GEMM start offsets (ms after the run began) and durations of the LAST run; returns
+ * the number of entries written.  Diagnostics for the exposed-broadcast measurement. */
+int phpc_summa_timeline(phpc_summa *s, float *start_ms, float *dur_ms, int max_steps);
 /* Host-sourced run (what phpc_gemm_summa_cuda does): C += A*B on FULL N x N host matrices,
  * owned chunks uploaded on a copy stream while earlier chunks compute, C block downloaded
  * (and gathered to rank 0 when gather != 0) at the end.  Synchronous. */

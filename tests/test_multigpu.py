@@ -65,6 +65,16 @@ def test_golden_reference_summa_fixture(gpu, oracle, tmp_path):
         assert oracle.rel_frobenius(C, g["summa_N48_P4_F1"]) <= 1e-14
 
 
+def test_nccl_broadcast_transport_equals_pull_transport(gpu, oracle, tmp_path):
+    """PHPC_PANEL=nccl (ncclBroadcast on row/column communicators) vs the default copy-engine pull:
+    the same chunks reach the same GEMMs, so the results are bit-identical."""
+    _need(gpu, 2)
+    grid = (2, 2) if gpu.phpc_b200_device_count() >= 4 else (1, 2)
+    a, _ = _run(grid, 384, 1, tmp_path, kc=50)
+    b, _ = _run(grid, 384, 1, tmp_path, kc=50, env={"PHPC_PANEL": "nccl"})
+    assert np.array_equal(a, b)
+
+
 def test_mpi_gather_path_equals_nvlink_gather(gpu, oracle, tmp_path):
     _need(gpu, 2)
     a, _ = _run((1, 2), 256, 1, tmp_path)
