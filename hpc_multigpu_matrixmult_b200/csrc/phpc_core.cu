@@ -30,6 +30,8 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static encode_tiled_fn g_encode_tiled = nullptr;
+typedef CUresult (*addr_range_fn)(CUdeviceptr *, size_t *, CUdeviceptr);
+static addr_range_fn g_addr_range = nullptr;
 
 static void load_driver_entry_points() {
   if (g_encode_tiled) return;
@@ -38,6 +40,19 @@ static void load_driver_entry_points() {
   CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   PHPC_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "driver has no cuTensorMapEncodeTiled (need CUDA 12+ driver)");
   g_encode_tiled = (encode_tiled_fn)fn;
+  fn = nullptr;
+  CUDA_CHECK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+  PHPC_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "driver has no cuMemGetAddressRange");
+  g_addr_range = (addr_range_fn)fn;
+}
+
+long long phpc_offset_in_allocation(const void *dptr) {
+  load_driver_entry_points();
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  CUresult r = g_addr_range(&base, &size, (CUdeviceptr)dptr);
+  if (r != CUDA_SUCCESS) phpc_die("cuMemGetAddressRange", "not a device allocation", __FILE__, __LINE__);
+  return (long long)((CUdeviceptr)dptr - base);
 }
 
 DeviceCtx *phpc_ctx(int device) {

@@ -63,4 +63,7 @@ int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const doub
 void phpc_launch_cublas(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                         int k, int n, cudaStream_t stream);
 
+/* byte offset of a device pointer inside the cudaMalloc allocation that contains it */
+long long phpc_offset_in_allocation(const void *dptr);
+
 static inline long long phpc_pad_ld(long long cols) { return (cols + 15) / 16 * 16; }

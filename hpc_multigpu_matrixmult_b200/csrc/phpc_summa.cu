@@ -13,7 +13,9 @@
  */
 #include <mpi.h>
 #include <nccl.h>
+#include <stdint.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <vector>
 
@@ -35,6 +37,33 @@ static int gcd_int(int a, int b) {
     b = t;
   }
   return a;
+}
+
+#include <sys/time.h>
+static double now_s() {
+  struct timeval tv;
+  gettimeofday(&tv, nullptr);
+  return tv.tv_sec + tv.tv_usec * 1e-6;
+}
+#define PHPC_TRACE(rank, what, t0)                                                         \
+  do {                                                                                     \
+    if (getenv("PHPC_DEBUG")) fprintf(stderr, "[phpc %d] %-28s %.3f s\n", rank, what, now_s() - (t0)); \
+  } while (0)
+
+__global__ void debug_sum_kernel(const double *p, size_t n, double *out) {
+  double acc = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += p[i];
+  atomicAdd(out, acc);
+}
+static double debug_sum(const double *p, size_t n, cudaStream_t st) {
+  double *d, h = 0;
+  cudaMalloc(&d, 8);
+  cudaMemsetAsync(d, 0, 8, st);
+  debug_sum_kernel<<<64, 256, 0, st>>>(p, n, d);
+  cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  cudaFree(d);
+  return h;
 }
 
 static int env_int(const char *name, int dflt) {
@@ -144,6 +173,7 @@ struct phpc_summa {
    * owner's store through CUDA IPC peer mappings (no SMs, no rendezvous) */
   int transport = 0;
   std::vector<double *> peerA, peerB;        /* peerA[pj'] = dA of rank (pi, pj'); peerB[pi'] = dB of rank (pi', pj) */
+  std::vector<void *> peerA_base, peerB_base; /* what cudaIpcOpenMemHandle returned (allocation bases) */
   std::vector<long long> root_a_off, root_b_off; /* per step: chunk offset inside its ROOT's store */
   std::vector<cudaEvent_t> ev_bcast2;        /* per ring slot: B pull done (pull transport) */
   size_t ringA_elems = 0, ringB_elems = 0;
@@ -191,17 +221,32 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   s->steps.resize(nsteps);
   phpc_summa_schedule(n, s->r, s->c, s->pi, s->pj, kc, s->steps.data(), nsteps, nullptr, nullptr);
 
+  double t0 = now_s();
   phpc_b200_set_device(pick_device(s->rank));
   s->ctx = phpc_cur_ctx();
+  PHPC_TRACE(s->rank, "create: device context", t0);
+  t0 = now_s();
   nccl_grid_get(grid_comm, s->size, s->rank, s->r, s->c, s->pi, s->pj);
+  PHPC_TRACE(s->rank, "create: nccl communicators", t0);
+  t0 = now_s();
 
   /* owned blocks: A chunks back to back ([m][pad(width)] each), B panels [pk][ldn] back to back, C [m][ldn] */
   for (const phpc_summa_step &st : s->steps)
     if (st.own_a) s->a_elems += (size_t)s->m * phpc_pad_ld(st.width);
   s->b_elems = (size_t)(s->lcm / s->r) * s->pk * s->ldn;
   s->c_elems = (size_t)s->m * s->ldn;
-  CUDA_CHECK(cudaMalloc(&s->dA, (s->a_elems ? s->a_elems : 2) * sizeof(double)));
-  CUDA_CHECK(cudaMalloc(&s->dB, (s->b_elems ? s->b_elems : 2) * sizeof(double)));
+  /* The A and B stores are exported through CUDA IPC.  An IPC handle maps the whole backing
+   * allocation, and cudaMalloc packs requests under 1 MiB into shared 2 MiB blocks, so the
+   * stores are rounded up to whole 2 MiB granules: each is then its own, granule-aligned
+   * allocation and the imported pointer is the store itself. */
+  const size_t granule = (size_t)2 << 20;
+  const size_t a_tag_off = ((s->a_elems ? s->a_elems : 2) * sizeof(double) + 255) / 256 * 256; /* 8-byte mapping tag after the data */
+  const size_t b_tag_off = ((s->b_elems ? s->b_elems : 2) * sizeof(double) + 255) / 256 * 256;
+  const size_t a_bytes = (a_tag_off + 256 + granule - 1) / granule * granule;
+  const size_t b_bytes = (b_tag_off + 256 + granule - 1) / granule * granule;
+  CUDA_CHECK(cudaMalloc(&s->dA, a_bytes));
+  CUDA_CHECK(cudaMalloc(&s->dB, b_bytes));
+  PHPC_REQUIRE(((uintptr_t)s->dA % granule) == 0 && ((uintptr_t)s->dB % granule) == 0, "IPC-exported stores must be 2 MiB aligned");
   CUDA_CHECK(cudaMalloc(&s->dC, s->c_elems * sizeof(double)));
   CUDA_CHECK(cudaMemset(s->dC, 0, s->c_elems * sizeof(double)));
 
@@ -227,23 +272,64 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   }
   if (s->size > 1 && s->transport == 1) {
     /* exchange CUDA IPC handles of the A and B stores over the control plane */
+    /* Opening the handle of a cudaMalloc base pointer yields the mapping of that pointer (the
+     * stores are whole 2 MiB granules, see above).  Every mapping is verified before use: the
+     * exporter plants a random tag behind its data, the importer must read the same tag through
+     * its mapping, otherwise the process aborts instead of multiplying the wrong memory. */
     struct Handles {
       cudaIpcMemHandle_t a, b;
+      unsigned long long a_tag, b_tag;
+      unsigned long long a_tag_off, b_tag_off;
     };
     std::vector<Handles> all(s->size);
+    memset(all.data(), 0, sizeof(Handles) * all.size());
     CUDA_CHECK(cudaIpcGetMemHandle(&all[s->rank].a, s->dA));
     CUDA_CHECK(cudaIpcGetMemHandle(&all[s->rank].b, s->dB));
+    {
+      const unsigned long long salt = (unsigned long long)(now_s() * 1e6) ^ ((unsigned long long)getpid() << 32);
+      all[s->rank].a_tag = salt * 0x9E3779B97F4A7C15ull + (unsigned long long)(uintptr_t)s->dA;
+      all[s->rank].b_tag = salt * 0xBF58476D1CE4E5B9ull + (unsigned long long)(uintptr_t)s->dB;
+      all[s->rank].a_tag_off = a_tag_off;
+      all[s->rank].b_tag_off = b_tag_off;
+      CUDA_CHECK(cudaMemcpy((char *)s->dA + a_tag_off, &all[s->rank].a_tag, 8, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy((char *)s->dB + b_tag_off, &all[s->rank].b_tag, 8, cudaMemcpyHostToDevice));
+    }
     for (int root = 0; root < s->size; ++root) MPI_Bcast(&all[root], (int)sizeof(Handles), MPI_BYTE, root, grid_comm);
     s->peerA.assign(s->c, nullptr);
     s->peerB.assign(s->r, nullptr);
+    if (getenv("PHPC_DEBUG_SUMS")) {
+      const unsigned long long *w = (const unsigned long long *)&all[s->rank].a;
+      fprintf(stderr, "[phpc %d] export dA=%p handle=%016llx %016llx %016llx %016llx alloc_off=%lld\n", s->rank, (void *)s->dA, w[0], w[1],
+              w[2], w[3], phpc_offset_in_allocation(s->dA));
+    }
+    s->peerA_base.assign(s->c, nullptr);
+    s->peerB_base.assign(s->r, nullptr);
     for (int pj2 = 0; pj2 < s->c; ++pj2)
-      if (pj2 != s->pj)
-        CUDA_CHECK(cudaIpcOpenMemHandle((void **)&s->peerA[pj2], all[s->pi * s->c + pj2].a, cudaIpcMemLazyEnablePeerAccess));
+      if (pj2 != s->pj) {
+        const Handles &h = all[s->pi * s->c + pj2];
+        CUDA_CHECK(cudaIpcOpenMemHandle(&s->peerA_base[pj2], h.a, cudaIpcMemLazyEnablePeerAccess));
+        s->peerA[pj2] = (double *)s->peerA_base[pj2];
+        unsigned long long seen = 0;
+        CUDA_CHECK(cudaMemcpy(&seen, (char *)s->peerA_base[pj2] + h.a_tag_off, 8, cudaMemcpyDeviceToHost));
+        PHPC_REQUIRE(seen == h.a_tag, "CUDA IPC mapping of a peer's A store does not show the peer's tag");
+        if (getenv("PHPC_DEBUG_SUMS")) {
+          const unsigned long long *w = (const unsigned long long *)&h.a;
+          fprintf(stderr, "[phpc %d] import from col %d handle=%016llx %016llx %016llx %016llx -> %p\n", s->rank, pj2, w[0], w[1], w[2], w[3],
+                  s->peerA_base[pj2]);
+        }
+      }
     for (int pi2 = 0; pi2 < s->r; ++pi2)
-      if (pi2 != s->pi)
-        CUDA_CHECK(cudaIpcOpenMemHandle((void **)&s->peerB[pi2], all[pi2 * s->c + s->pj].b, cudaIpcMemLazyEnablePeerAccess));
+      if (pi2 != s->pi) {
+        const Handles &h = all[pi2 * s->c + s->pj];
+        CUDA_CHECK(cudaIpcOpenMemHandle(&s->peerB_base[pi2], h.b, cudaIpcMemLazyEnablePeerAccess));
+        s->peerB[pi2] = (double *)s->peerB_base[pi2];
+        unsigned long long seen = 0;
+        CUDA_CHECK(cudaMemcpy(&seen, (char *)s->peerB_base[pi2] + h.b_tag_off, 8, cudaMemcpyDeviceToHost));
+        PHPC_REQUIRE(seen == h.b_tag, "CUDA IPC mapping of a peer's B store does not show the peer's tag");
+      }
   }
 
+  PHPC_TRACE(s->rank, "create: blocks + ipc", t0);
   s->nbuf = env_int("PHPC_NBUF", 3);
   if (s->nbuf < 2) s->nbuf = 2;
   if (s->c > 1) {
@@ -279,14 +365,17 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
 
 extern "C" void phpc_summa_destroy(phpc_summa *s) {
   if (!s) return;
+  const double t0 = now_s();
+  const int rank_dbg = s->rank;
   CUDA_CHECK(cudaSetDevice(s->ctx->device));
   CUDA_CHECK(cudaDeviceSynchronize());
   if (s->size > 1 && s->transport == 1) {
     MPI_Barrier(s->grid_comm); /* nobody is still pulling from the stores freed below */
-    for (double *p : s->peerA)
+    for (void *p : s->peerA_base)
       if (p) cudaIpcCloseMemHandle(p);
-    for (double *p : s->peerB)
+    for (void *p : s->peerB_base)
       if (p) cudaIpcCloseMemHandle(p);
+    MPI_Barrier(s->grid_comm); /* every importer has unmapped before the exporter frees */
   }
   for (cudaEvent_t e : s->ev_bcast2) cudaEventDestroy(e);
   cudaFree(s->dA);
@@ -305,6 +394,7 @@ extern "C" void phpc_summa_destroy(phpc_summa *s) {
   cudaEventDestroy(s->ev_end);
   cudaEventDestroy(s->ev_user);
   delete s;
+  PHPC_TRACE(rank_dbg, "destroy", t0);
 }
 
 extern "C" void phpc_summa_geometry(const phpc_summa *s, int dims[2], int coords[2], int block[2]) {
@@ -495,6 +585,12 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
     }
     CUDA_CHECK(cudaEventRecord(s->ev_g1[q], comp));
     if (any_comm) CUDA_CHECK(cudaEventRecord(s->ev_free[slot], comp));
+    if (getenv("PHPC_DEBUG_SUMS")) { /* serialising diagnostic: what did this step multiply? */
+      CUDA_CHECK(cudaDeviceSynchronize());
+      const double sa = debug_sum(a, (size_t)s->m * lda, comp), sb = debug_sum(b, (size_t)st.width * s->ldn, comp);
+      fprintf(stderr, "[phpc %d] step %d own_a=%d own_b=%d slot=%d a=%p sumA=%.6e sumB=%.6e root_a_off=%lld\n", s->rank, q, st.own_a,
+              st.own_b, slot, (const void *)a, sa, sb, s->root_a_off[q]);
+    }
     /* prefetch: the stage-in of the next nbuf-1 steps runs under this GEMM */
     while (issued < nsteps && issued < q + s->nbuf) stage_in(issued++);
   }

@@ -72,7 +72,11 @@ def test_nccl_broadcast_transport_equals_pull_transport(gpu, oracle, tmp_path):
     grid = (2, 2) if gpu.phpc_b200_device_count() >= 4 else (1, 2)
     a, _ = _run(grid, 384, 1, tmp_path, kc=50)
     b, _ = _run(grid, 384, 1, tmp_path, kc=50, env={"PHPC_PANEL": "nccl"})
-    assert np.array_equal(a, b)
+    for idx, name in ((0, "host-entry dmma"), (2, "device-resident dmma")):
+        diff = np.abs(a[idx] - b[idx])
+        assert np.array_equal(a[idx], b[idx]), f"{name}: {np.count_nonzero(diff)} elements differ, max {diff.max():.3e}"
+    # cuBLAS picks its kernel per call; only require agreement to rounding
+    assert oracle.rel_frobenius(a[1], b[1]) <= 1e-14
 
 
 def test_mpi_gather_path_equals_nvlink_gather(gpu, oracle, tmp_path):
