@@ -106,7 +106,20 @@ int main(int argc, char **argv) {
     const int code = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + WTERMSIG(st);
     if (code != 0 && rc == 0) {
       rc = code;
-      kill_all(SIGTERM); /* one rank failed: the job is over */
+      /* one rank failed: the job is over.  Ranks that abort together (MPI_Abort on every rank,
+       * rank 0 printing the reason) get half a second to finish on their own first. */
+      for (int spin = 0; spin < 50 && left > 0; ++spin) {
+        int st2 = 0;
+        pid_t p2 = waitpid(-1, &st2, WNOHANG);
+        if (p2 > 0) {
+          --left;
+          for (int r = 0; r < n; ++r)
+            if (g_pids[r] == p2) g_pids[r] = 0;
+        } else {
+          usleep(10000);
+        }
+      }
+      kill_all(SIGTERM);
     }
   }
   if (n > 1) phpc_mpi_segment_unlink(g_path);
