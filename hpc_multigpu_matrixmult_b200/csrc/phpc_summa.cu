@@ -136,6 +136,11 @@ static void nccl_grid_get(MPI_Comm grid_comm, int size, int rank, int r, int c, 
   g_nccl.c = c;
   g_nccl.rank = rank;
   if (size > 1) {
+    /* one node, NVLink only: do not let NCCL probe InfiniBand / every NIC or set up NVLS
+     * multicast for communicators that only broadcast (user settings win) */
+    setenv("NCCL_IB_DISABLE", "1", 0);
+    setenv("NCCL_SOCKET_IFNAME", "lo", 0);
+    setenv("NCCL_NVLS_ENABLE", "0", 0);
     ncclUniqueId id;
     memset(&id, 0, sizeof id);
     if (rank == 0) NCCL_CHECK(ncclGetUniqueId(&id));
@@ -174,6 +179,7 @@ struct phpc_summa {
   int transport = 0;
   std::vector<double *> peerA, peerB;        /* peerA[pj'] = dA of rank (pi, pj'); peerB[pi'] = dB of rank (pi', pj) */
   std::vector<void *> peerA_base, peerB_base; /* what cudaIpcOpenMemHandle returned (allocation bases) */
+  std::vector<void *> peerC;                  /* rank 0 only: dC of every other rank */
   std::vector<long long> root_a_off, root_b_off; /* per step: chunk offset inside its ROOT's store */
   std::vector<cudaEvent_t> ev_bcast2;        /* per ring slot: B pull done (pull transport) */
   size_t ringA_elems = 0, ringB_elems = 0;
@@ -225,8 +231,12 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   phpc_b200_set_device(pick_device(s->rank));
   s->ctx = phpc_cur_ctx();
   PHPC_TRACE(s->rank, "create: device context", t0);
+  {
+    const char *t = getenv("PHPC_PANEL");
+    s->transport = (s->size > 1 && !(t && !strcmp(t, "nccl"))) ? 1 : 0;
+  }
   t0 = now_s();
-  nccl_grid_get(grid_comm, s->size, s->rank, s->r, s->c, s->pi, s->pj);
+  if (s->size > 1 && s->transport == 0) nccl_grid_get(grid_comm, s->size, s->rank, s->r, s->c, s->pi, s->pj);
   PHPC_TRACE(s->rank, "create: nccl communicators", t0);
   t0 = now_s();
 
@@ -247,7 +257,10 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   CUDA_CHECK(cudaMalloc(&s->dA, a_bytes));
   CUDA_CHECK(cudaMalloc(&s->dB, b_bytes));
   PHPC_REQUIRE(((uintptr_t)s->dA % granule) == 0 && ((uintptr_t)s->dB % granule) == 0, "IPC-exported stores must be 2 MiB aligned");
-  CUDA_CHECK(cudaMalloc(&s->dC, s->c_elems * sizeof(double)));
+  const size_t c_tag_off = (s->c_elems * sizeof(double) + 255) / 256 * 256;
+  const size_t c_bytes = (c_tag_off + 256 + granule - 1) / granule * granule;
+  CUDA_CHECK(cudaMalloc(&s->dC, c_bytes));
+  PHPC_REQUIRE(((uintptr_t)s->dC % granule) == 0, "IPC-exported stores must be 2 MiB aligned");
   CUDA_CHECK(cudaMemset(s->dC, 0, s->c_elems * sizeof(double)));
 
   /* where every chunk lives on the rank that owns it (needed to pull it) */
@@ -266,10 +279,6 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
         if (tmp[q].own_b) s->root_b_off[q] = tmp[q].b_off;
     }
   }
-  {
-    const char *t = getenv("PHPC_PANEL");
-    s->transport = (s->size > 1 && !(t && !strcmp(t, "nccl"))) ? 1 : 0;
-  }
   if (s->size > 1 && s->transport == 1) {
     /* exchange CUDA IPC handles of the A and B stores over the control plane */
     /* Opening the handle of a cudaMalloc base pointer yields the mapping of that pointer (the
@@ -277,20 +286,24 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
      * exporter plants a random tag behind its data, the importer must read the same tag through
      * its mapping, otherwise the process aborts instead of multiplying the wrong memory. */
     struct Handles {
-      cudaIpcMemHandle_t a, b;
-      unsigned long long a_tag, b_tag;
-      unsigned long long a_tag_off, b_tag_off;
+      cudaIpcMemHandle_t a, b, c;
+      unsigned long long a_tag, b_tag, c_tag;
+      unsigned long long a_tag_off, b_tag_off, c_tag_off;
     };
     std::vector<Handles> all(s->size);
     memset(all.data(), 0, sizeof(Handles) * all.size());
     CUDA_CHECK(cudaIpcGetMemHandle(&all[s->rank].a, s->dA));
     CUDA_CHECK(cudaIpcGetMemHandle(&all[s->rank].b, s->dB));
+    CUDA_CHECK(cudaIpcGetMemHandle(&all[s->rank].c, s->dC));
     {
       const unsigned long long salt = (unsigned long long)(now_s() * 1e6) ^ ((unsigned long long)getpid() << 32);
       all[s->rank].a_tag = salt * 0x9E3779B97F4A7C15ull + (unsigned long long)(uintptr_t)s->dA;
       all[s->rank].b_tag = salt * 0xBF58476D1CE4E5B9ull + (unsigned long long)(uintptr_t)s->dB;
+      all[s->rank].c_tag = salt * 0x94D049BB133111EBull + (unsigned long long)(uintptr_t)s->dC;
       all[s->rank].a_tag_off = a_tag_off;
       all[s->rank].b_tag_off = b_tag_off;
+      all[s->rank].c_tag_off = c_tag_off;
+      CUDA_CHECK(cudaMemcpy((char *)s->dC + c_tag_off, &all[s->rank].c_tag, 8, cudaMemcpyHostToDevice));
       CUDA_CHECK(cudaMemcpy((char *)s->dA + a_tag_off, &all[s->rank].a_tag, 8, cudaMemcpyHostToDevice));
       CUDA_CHECK(cudaMemcpy((char *)s->dB + b_tag_off, &all[s->rank].b_tag, 8, cudaMemcpyHostToDevice));
     }
@@ -327,6 +340,15 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
         CUDA_CHECK(cudaMemcpy(&seen, (char *)s->peerB_base[pi2] + h.b_tag_off, 8, cudaMemcpyDeviceToHost));
         PHPC_REQUIRE(seen == h.b_tag, "CUDA IPC mapping of a peer's B store does not show the peer's tag");
       }
+    if (s->rank == 0) { /* the gather root reads every C block */
+      s->peerC.assign(s->size, nullptr);
+      for (int i = 1; i < s->size; ++i) {
+        CUDA_CHECK(cudaIpcOpenMemHandle(&s->peerC[i], all[i].c, cudaIpcMemLazyEnablePeerAccess));
+        unsigned long long seen = 0;
+        CUDA_CHECK(cudaMemcpy(&seen, (char *)s->peerC[i] + all[i].c_tag_off, 8, cudaMemcpyDeviceToHost));
+        PHPC_REQUIRE(seen == all[i].c_tag, "CUDA IPC mapping of a peer's C block does not show the peer's tag");
+      }
+    }
   }
 
   PHPC_TRACE(s->rank, "create: blocks + ipc", t0);
@@ -374,6 +396,8 @@ extern "C" void phpc_summa_destroy(phpc_summa *s) {
     for (void *p : s->peerA_base)
       if (p) cudaIpcCloseMemHandle(p);
     for (void *p : s->peerB_base)
+      if (p) cudaIpcCloseMemHandle(p);
+    for (void *p : s->peerC)
       if (p) cudaIpcCloseMemHandle(p);
     MPI_Barrier(s->grid_comm); /* every importer has unmapped before the exporter frees */
   }
@@ -690,9 +714,14 @@ extern "C" void phpc_summa_download_c(phpc_summa *s, double *C, int gather) {
   /* own block -> own place (every rank keeps its block at its global offset, reference :44) */
   CUDA_CHECK(cudaMemcpy2DAsync(C + (size_t)s->pi * s->m * N + (size_t)s->pj * s->n, N * sizeof(double), s->dC, s->ldn * sizeof(double),
                                row_bytes, s->m, cudaMemcpyDeviceToHost, st));
-  if (s->rank != 0) {
+  if (s->transport == 1) {
+    /* pull transport: the root copies each peer's finished C block out of the peer's HBM */
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    MPI_Barrier(s->grid_comm); /* every block is final */
+  } else if (s->rank != 0) {
     NCCL_CHECK(ncclSend(s->dC, s->c_elems, ncclDouble, 0, g_nccl.world, st));
-  } else {
+  }
+  if (s->rank == 0) {
     if (!s->gather_stage) CUDA_CHECK(cudaMalloc(&s->gather_stage, 2 * s->c_elems * sizeof(double)));
     cudaEvent_t drained[2];
     for (int b = 0; b < 2; ++b) CUDA_CHECK(cudaEventCreateWithFlags(&drained[b], cudaEventDisableTiming));
@@ -702,7 +731,10 @@ extern "C" void phpc_summa_download_c(phpc_summa *s, double *C, int gather) {
       const int b = i & 1;
       double *stage = s->gather_stage + (size_t)b * s->c_elems;
       if (i > 2) CUDA_CHECK(cudaStreamWaitEvent(st, drained[b], 0));
-      NCCL_CHECK(ncclRecv(stage, s->c_elems, ncclDouble, i, g_nccl.world, st));
+      if (s->transport == 1)
+        CUDA_CHECK(cudaMemcpyAsync(stage, s->peerC[i], s->c_elems * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      else
+        NCCL_CHECK(ncclRecv(stage, s->c_elems, ncclDouble, i, g_nccl.world, st));
       CUDA_CHECK(cudaEventRecord(s->ev_user, st));
       CUDA_CHECK(cudaStreamWaitEvent(ctx->copy, s->ev_user, 0));
       CUDA_CHECK(cudaMemcpy2DAsync(C + N * (size_t)co[0] * s->m + (size_t)co[1] * s->n, N * sizeof(double), stage,
@@ -713,6 +745,7 @@ extern "C" void phpc_summa_download_c(phpc_summa *s, double *C, int gather) {
     for (int b = 0; b < 2; ++b) CUDA_CHECK(cudaEventDestroy(drained[b]));
   }
   CUDA_CHECK(cudaStreamSynchronize(st));
+  if (s->transport == 1) MPI_Barrier(s->grid_comm); /* the root is done reading before anyone touches its block */
 }
 
 /* ------------------------------------------------------------------------- */
