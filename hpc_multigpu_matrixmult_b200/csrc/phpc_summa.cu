@@ -480,6 +480,7 @@ extern "C" void phpc_summa_fill(phpc_summa *s, int kind, unsigned long long seed
   }
   CUDA_CHECK(cudaMemsetAsync(s->dC, 0, s->c_elems * sizeof(double), st));
   CUDA_CHECK(cudaStreamSynchronize(st));
+  if (s->size > 1) MPI_Barrier(s->grid_comm); /* every store is valid before anyone pulls from it */
 }
 
 /* ------------------------------------------------------------------------- */

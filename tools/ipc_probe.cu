@@ -1,4 +1,6 @@
 // ipc_probe.cu — CUDA IPC peer-pull sanity check under the MPI shim (2 ranks, 2 GPUs).
+// Variants: data written by a kernel BEFORE the peer opens the mapping, AFTER it (what the SUMMA
+// stores do: export at create, fill later), and after with an H2D copy instead of a kernel.
 #include <cuda_runtime.h>
 #include <mpi.h>
 #include <stdio.h>
@@ -11,22 +13,26 @@ __global__ void fillk(double* p, size_t n, double v){ for(size_t i=blockIdx.x*(s
 int main(int argc,char**argv){
   int rank,size; MPI_Init(&argc,&argv); MPI_Comm_rank(MPI_COMM_WORLD,&rank); MPI_Comm_size(MPI_COMM_WORLD,&size);
   CK(cudaSetDevice(rank)); CK(cudaFree(0));
-  size_t sizes[3]={ (size_t)300<<10, (size_t)2<<20, (size_t)64<<20 };
-  for(int t=0;t<3;++t){
-    size_t bytes=sizes[t], n=bytes/8; double *mine,*other_small; 
-    CK(cudaMalloc(&other_small, 4096)); CK(cudaMalloc(&mine,bytes));
-    fillk<<<64,256>>>(mine,n,1000.0*(rank+1)); CK(cudaDeviceSynchronize());
+  cudaStream_t s, s2; CK(cudaStreamCreateWithFlags(&s,cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&s2,cudaStreamNonBlocking));
+  size_t bytes=(size_t)2<<20, n=bytes/8;
+  for(int variant=0; variant<4; ++variant){
+    double *mine; CK(cudaMalloc(&mine,bytes)); CK(cudaMemset(mine,0,bytes));
+    if(variant==0){ fillk<<<64,256,0,s2>>>(mine,n,1000.0*(rank+1)); CK(cudaStreamSynchronize(s2)); }
     cudaIpcMemHandle_t h[2]; CK(cudaIpcGetMemHandle(&h[rank],mine));
     for(int r=0;r<2;++r) MPI_Bcast(&h[r],sizeof(h[r]),MPI_BYTE,r,MPI_COMM_WORLD);
-    double t0=now(); void* peer; CK(cudaIpcOpenMemHandle(&peer,h[1-rank],cudaIpcMemLazyEnablePeerAccess)); double t_open=now()-t0;
-    double* dst; CK(cudaMalloc(&dst,bytes)); CK(cudaMemset(dst,0,bytes));
-    cudaStream_t s; CK(cudaStreamCreateWithFlags(&s,cudaStreamNonBlocking));
+    void* peer; CK(cudaIpcOpenMemHandle(&peer,h[1-rank],cudaIpcMemLazyEnablePeerAccess));
+    double probe=0; CK(cudaMemcpy(&probe,(char*)peer+bytes-8,8,cudaMemcpyDeviceToHost)); // like the tag check
+    if(variant==1||variant==3){ fillk<<<64,256,0,s2>>>(mine,n,1000.0*(rank+1)); CK(cudaStreamSynchronize(s2)); }
+    if(variant==2){ std::vector<double> hb(n); for(size_t i=0;i<n;++i) hb[i]=1000.0*(rank+1)+i; CK(cudaMemcpy(mine,hb.data(),bytes,cudaMemcpyHostToDevice)); }
+    if(variant==3){ CK(cudaDeviceSynchronize()); }
+    double* dst; CK(cudaMalloc(&dst,bytes)); CK(cudaMemset(dst,0,bytes)); CK(cudaDeviceSynchronize());
     MPI_Barrier(MPI_COMM_WORLD);
-    t0=now(); CK(cudaMemcpyAsync(dst,peer,bytes,cudaMemcpyDeviceToDevice,s)); CK(cudaStreamSynchronize(s)); double t_copy=now()-t0;
+    double t0=now(); CK(cudaMemcpyAsync(dst,peer,bytes,cudaMemcpyDeviceToDevice,s)); CK(cudaStreamSynchronize(s)); double t_copy=now()-t0;
     std::vector<double> hbuf(n); CK(cudaMemcpy(hbuf.data(),dst,bytes,cudaMemcpyDeviceToHost));
     size_t bad=0; for(size_t i=0;i<n;++i) if(hbuf[i]!=1000.0*(2-rank)+i) ++bad;
-    printf("[%d] size %zu KiB: open %.3f s, copy %.3f ms (%.1f GB/s), bad=%zu first=%.1f\n",rank,bytes>>10,t_open,t_copy*1e3,bytes/t_copy/1e9,bad,hbuf[0]);
+    const char* names[4]={"kernel fill BEFORE open","kernel fill AFTER open","H2D copy AFTER open","kernel fill AFTER open + device sync"};
+    printf("[%d] %-40s copy %.3f ms bad=%zu first=%.1f\n",rank,names[variant],t_copy*1e3,bad,hbuf[0]);
     MPI_Barrier(MPI_COMM_WORLD);
-    CK(cudaIpcCloseMemHandle(peer)); MPI_Barrier(MPI_COMM_WORLD); CK(cudaFree(mine)); CK(cudaFree(dst)); CK(cudaFree(other_small));
+    CK(cudaIpcCloseMemHandle(peer)); MPI_Barrier(MPI_COMM_WORLD); CK(cudaFree(mine)); CK(cudaFree(dst));
   }
   MPI_Finalize(); return 0; }
