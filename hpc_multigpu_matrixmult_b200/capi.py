@@ -22,7 +22,7 @@ c_double_p = ctypes.POINTER(ctypes.c_double)
 c_float_p = ctypes.POINTER(ctypes.c_float)
 c_int_p = ctypes.POINTER(ctypes.c_int)
 
-BACKEND_DMMA, BACKEND_CUBLAS = 0, 1
+BACKEND_DMMA, BACKEND_CUBLAS, BACKEND_OZAKI = 0, 1, 2
 FILL_INDEX, FILL_SEEDED = 0, 1
 SEED_A, SEED_B = 1234, 5678
 
@@ -104,6 +104,8 @@ def load():
     dev_gemm = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_int] * 3
     L.phpc_gemm_device.argtypes = dev_gemm + [ctypes.c_int, ctypes.c_void_p]
     L.phpc_gemm_device.restype = ctypes.c_int
+    L.phpc_gemm_device_ozaki.argtypes = dev_gemm + [ctypes.c_int, ctypes.c_void_p]
+    L.phpc_gemm_device_ozaki.restype = ctypes.c_int
     L.phpc_gemm_device_cublas.argtypes = dev_gemm + [ctypes.c_void_p]
     L.phpc_gemm_device_cublas.restype = None
     L.phpc_gemm_device_timed.argtypes = dev_gemm + [ctypes.c_int, ctypes.c_int, ctypes.c_int]

@@ -1,0 +1,260 @@
+/*
+ * ozaki_gemm.cuh — FP64 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM).
+ *
+ * tcgen05.mma has no FP64 kind, so the FP64 product is rebuilt EXACTLY from integer
+ * products (the Ozaki scheme): every row of A and every column of B is scaled by a
+ * power of two and cut into S signed 7-bit digits (ozaki_split.cuh),
+ *     a_ik = 2^eA[i] * sum_t A_t[i][k] * 2^(-7t),   b_kj = 2^eB[j] * sum_u B_u[k][j] * 2^(-7u),
+ * the digit matrices are multiplied on the int8 tensor pipe with exact int32
+ * accumulation in TMEM (|A_t.B_u| <= K * 127^2, no rounding at all), and
+ *     C[i][j] += 2^(eA[i]+eB[j]) * sum_g 2^(-7g) * P_g[i][j],   P_g = sum_{t+u=g} A_t.B_u
+ * is applied in FP64 by the epilogue warps, least significant group first.  Groups with
+ * g > S+1 are dropped (their weight is below 2^(-7(S+1)) of the row/column scale), so
+ * S(S+1)/2 int8 MMAs stand for one FP64 MMA; S = 8 carries 56 bits.
+ *
+ * Kernel (one CTA per SM, persistent over 128 x 256 output tiles, static round robin):
+ *   warp 0      TMA producer: A_t tile [128 rows][128 B of k] + B_u tile [256 rows][128 B of k]
+ *               per stage (both K-major, 128-byte swizzle), 4-stage mbarrier ring
+ *   warp 1      TMEM allocator + MMA issuer: one lane issues tcgen05.mma.kind::i8 128x256x32,
+ *               all pairs (t,u) of a group accumulate into the same TMEM accumulator;
+ *               tcgen05.commit frees smem stages / publishes the accumulator
+ *   warps 2-5   epilogue: tcgen05.ld the int32 accumulator (two 256-column TMEM buffers, so the
+ *               epilogue of group g overlaps the MMAs of group g-1), convert, scale, C +=
+ * The reference kernel this replaces is gemm_kernel of src/phpc_gemm.cu:6-57 (same C += A.B
+ * contract); the arithmetic differs from it only in the order of the exact partial sums.
+ */
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dmma_gemm.cuh" /* mbarrier / TMA wrappers, tile_coords */
+
+namespace phpc {
+namespace oz {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BKB = 128; /* bytes (= int8 elements) of k per stage: one 128-byte swizzle row */
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BKB;
+constexpr int B_BYTES = BN * BKB;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int THREADS = 192; /* warp 0 TMA, warp 1 MMA, warps 2-5 epilogue */
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int TMEM_COLS = 512; /* two int32 accumulators of 256 columns */
+constexpr int DIGIT_BITS = 7;
+constexpr int MAX_SLICES = 8;
+constexpr int ZERO_EXP = -2147483647 - 1; /* exponent of an all-zero row / column */
+
+struct Params {
+  double *C;
+  long long ldc;
+  int M, N;    /* rows of A / C, columns of B / C (rows per digit matrix in the slice stores) */
+  int kblocks; /* padded K / 128 */
+  int S;       /* digits per operand */
+  const int *eA;
+  const int *eB;
+  int tiles_m, tiles_n;
+};
+
+/* UMMA shared-memory descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart */
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  /* start address, 16-byte units */
+  d |= (uint64_t)1 << 16;                   /* leading byte offset (unused for swizzled K-major) */
+  d |= (uint64_t)(1024 >> 4) << 32;         /* stride byte offset between 8-row groups */
+  d |= (uint64_t)1 << 46;                   /* descriptor version (Blackwell) */
+  d |= (uint64_t)2 << 61;                   /* layout: SWIZZLE_128B */
+  return d;
+}
+
+/* instruction descriptor: s8 x s8 -> s32, A and B K-major, M = 128, N = 256 */
+__device__ __forceinline__ uint32_t idesc_i8(int m, int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, int (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+/* 2^e as a double (e clamped to the normal range; INT_MIN exponents mean "all zero") */
+__device__ __forceinline__ double pow2d(int e) {
+  e = max(-1022, min(1023, e));
+  return __hiloint2double((e + 1023) << 20, 0);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+    ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES;
+  const uint32_t tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
+  const uint32_t tmem_slot = tempty0 + 16; /* 4 bytes: TMEM base address written by tcgen05.alloc */
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int S = p.S;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull0 + 8 * b, 1);
+      mbar_init(tempty0 + 8 * b, 4); /* one arrival per epilogue warp */
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    /* ===== TMA producer ===== */
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int tm, tn;
+        tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+        for (int g = S + 1; g >= 2; --g) {
+          const int t_lo = max(1, g - S), t_hi = min(S, g - 1);
+          for (int t = t_lo; t <= t_hi; ++t) {
+            const int u = g - t;
+            const int arow = (t - 1) * p.M + tm * BM;
+            const int brow = (u - 1) * p.N + tn * BN;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              mbar_wait(empty0 + 8 * stage, phase ^ 1);
+              const uint32_t full = full0 + 8 * stage;
+              mbar_expect_tx(full, STAGE_BYTES);
+              const uint32_t sa = smem_base + stage * STAGE_BYTES;
+              tma_load_2d(sa, &tmA, full, kb * BKB, arow);
+              tma_load_2d(sa + A_BYTES, &tmB, full, kb * BKB, brow);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    /* ===== MMA issuer: one lane, accumulators in TMEM ===== */
+    if (lane == 0) {
+      const uint32_t idesc = idesc_i8(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t unit = 0; /* counts (tile, group) units: TMEM buffer = unit & 1 */
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int g = S + 1; g >= 2; --g, ++unit) {
+          const uint32_t buf = unit & 1;
+          mbar_wait(tempty0 + 8 * buf, ((unit >> 1) & 1) ^ 1); /* epilogue drained this buffer */
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tacc = tmem_base + buf * BN;
+          const int pairs = min(S, g - 1) - max(1, g - S) + 1;
+          uint32_t accumulate = 0;
+          for (int it = 0; it < pairs * p.kblocks; ++it) {
+            mbar_wait(full0 + 8 * stage, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + A_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < BKB / 32; ++kk) {
+              umma_i8(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, accumulate); /* +32 bytes of k */
+              accumulate = 1;
+            }
+            umma_commit(empty0 + 8 * stage); /* smem stage reusable once these MMAs retire */
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(tfull0 + 8 * buf); /* accumulator of this group complete */
+        }
+      }
+    }
+  } else {
+    /* ===== epilogue: 4 warps, warp w reads TMEM lanes 32*(w%4) .. +31 ===== */
+    const int quarter = warp & 3;
+    uint32_t unit = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int tm, tn;
+      tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+      const int row = tm * BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int ea = row_ok ? p.eA[row] : ZERO_EXP;
+      double *crow = p.C + (long long)(row_ok ? row : 0) * p.ldc;
+      for (int g = S + 1; g >= 2; --g, ++unit) {
+        const uint32_t buf = unit & 1;
+        mbar_wait(tfull0 + 8 * buf, (unit >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
+        const int erow = ea - DIGIT_BITS * g;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          int v[16];
+          tmem_ld_32x32b_x16(taddr + c0, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const int col0 = tn * BN + c0;
+          if (row_ok && ea != ZERO_EXP && col0 < p.N) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = col0 + j;
+              if (col < p.N) {
+                const int eb = __ldg(p.eB + col);
+                if (eb != ZERO_EXP && v[j] != 0) crow[col] += (double)v[j] * pow2d(erow + eb); /* exact product, one rounding */
+              }
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace oz
+}  // namespace phpc

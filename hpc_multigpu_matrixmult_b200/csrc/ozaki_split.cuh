@@ -1,0 +1,129 @@
+/*
+ * ozaki_split.cuh — error-free splitting of FP64 operands into signed 7-bit digits.
+ *
+ * For a row i of A (a column j of B): e = 1 + floor(log2(max |x|)) so that |x| * 2^-e < 1, then
+ *     r_0 = x * 2^-e;   d_t = trunc(r_{t-1} * 128) in [-127, 127];   r_t = r_{t-1} * 128 - d_t
+ * Every step is exact in FP64 (scaling by powers of two, subtracting the integer part), so
+ *     x = 2^e * ( sum_{t=1..S} d_t * 2^(-7t) + r_S * 2^(-7S) ),   |r_S| < 1,
+ * i.e. S digits carry the top 7*S bits below the row/column maximum.  Digits are stored as
+ * K-major int8 matrices, one per t, back to back:
+ *     SA[t][i][k]  (m rows, row pitch kp bytes)        SB[u][j][k]  (n rows: B is transposed)
+ * kp = K rounded up to 128 with zero digits, which is what the UMMA K-major tiles want.
+ * HBM-bound streaming kernels: 8 bytes read, S bytes written per element.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ozaki_gemm.cuh"
+
+namespace phpc {
+namespace oz {
+
+__device__ __forceinline__ int exp_above(double x) { /* smallest e with |x| < 2^e; ZERO_EXP for 0 */
+  const int hi = __double2hiint(fabs(x));
+  const int lo = __double2loint(x);
+  if ((hi | lo) == 0) return ZERO_EXP;
+  const int biased = hi >> 20;
+  return biased == 0 ? -1022 : biased - 1023 + 1; /* denormals share the smallest normal exponent */
+}
+
+__global__ void exp_init_kernel(int *e, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) e[i] = ZERO_EXP;
+}
+
+/* eA[i] = max over the k columns of row i.  One warp per (row, 1024-column segment). */
+__global__ void row_exp_kernel(const double *__restrict__ A, long long lda, int m, int k, int *__restrict__ eA) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int segs = (k + 1023) / 1024;
+  const long long unit = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (unit >= (long long)m * segs) return;
+  const int row = (int)(unit / segs), seg = (int)(unit % segs);
+  const int lane = threadIdx.x & 31;
+  const double *p = A + (long long)row * lda;
+  int e = ZERO_EXP;
+  const int k_end = min(k, (seg + 1) * 1024);
+  for (int c = seg * 1024 + lane; c < k_end; c += 32) e = max(e, exp_above(p[c]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xffffffffu, e, o));
+  if (lane == 0 && e != ZERO_EXP) atomicMax(eA + row, e);
+}
+
+/* eB[j] = max over the k rows of column j.  Thread = column, block = 256 columns x 64-row band. */
+__global__ void col_exp_kernel(const double *__restrict__ B, long long ldb, int k, int n, int *__restrict__ eB) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n) return;
+  const int r0 = blockIdx.y * 64, r1 = min(k, r0 + 64);
+  int e = ZERO_EXP;
+  for (int r = r0; r < r1; ++r) e = max(e, exp_above(B[(long long)r * ldb + col]));
+  if (e != ZERO_EXP) atomicMax(eB + col, e);
+}
+
+__device__ __forceinline__ double scale_pow2(double x, int minus_e) { /* x * 2^-e, exact for normal results */
+  return scalbn(x, -minus_e);
+}
+
+/* A digits: thread = 16 consecutive k of one row -> one 16-byte store per digit matrix. */
+__global__ void split_a_kernel(const double *__restrict__ A, long long lda, int m, int k, int kp, const int *__restrict__ eA,
+                               int8_t *__restrict__ SA, int S) {
+  const int chunks = kp / 16;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)m * chunks) return;
+  const int row = (int)(idx / chunks), c0 = (int)(idx % chunks) * 16;
+  const int e = eA[row];
+  double r[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int c = c0 + j;
+    r[j] = (c < k && e != ZERO_EXP) ? scale_pow2(A[(long long)row * lda + c], e) : 0.0;
+  }
+  for (int t = 0; t < S; ++t) {
+    union {
+      int8_t b[16];
+      int4 v;
+    } out;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const double s = r[j] * 128.0;
+      const int d = (int)s; /* truncation toward zero */
+      r[j] = s - (double)d;
+      out.b[j] = (int8_t)d;
+    }
+    *reinterpret_cast<int4 *>(SA + ((long long)t * m + row) * kp + c0) = out.v;
+  }
+}
+
+/* B digits, transposed to K-major: thread = 32 consecutive k of one column (warp = 32 adjacent
+ * columns, so every B row read is a coalesced 256-byte line) -> one 32-byte sector per digit. */
+__global__ void split_b_kernel(const double *__restrict__ B, long long ldb, int k, int n, int kp, const int *__restrict__ eB,
+                               int8_t *__restrict__ SB, int S) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k0 = blockIdx.y * 32;
+  if (col >= n) return;
+  const int e = eB[col];
+  double r[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int row = k0 + j;
+    r[j] = (row < k && e != ZERO_EXP) ? scale_pow2(B[(long long)row * ldb + col], e) : 0.0;
+  }
+  for (int t = 0; t < S; ++t) {
+    union {
+      int8_t b[32];
+      int4 v[2];
+    } out;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const double s = r[j] * 128.0;
+      const int d = (int)s;
+      r[j] = s - (double)d;
+      out.b[j] = (int8_t)d;
+    }
+    int4 *dst = reinterpret_cast<int4 *>(SB + ((long long)t * n + col) * kp + k0);
+    dst[0] = out.v[0];
+    dst[1] = out.v[1];
+  }
+}
+
+}  // namespace oz
+}  // namespace phpc

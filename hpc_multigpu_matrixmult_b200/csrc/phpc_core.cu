@@ -9,6 +9,8 @@
 #include "../../include/phpc_b200.h"
 #include "../../include/phpc_gemm.cuh"
 #include "dmma_gemm.cuh"
+#include "ozaki_gemm.cuh"
+#include "ozaki_split.cuh"
 #include "phpc_internal.h"
 
 /* ------------------------------------------------------------------------- */
@@ -83,6 +85,7 @@ DeviceCtx *phpc_ctx(int device) {
   CUDA_CHECK(cudaEventCreate(&ctx->ev0));
   CUDA_CHECK(cudaEventCreate(&ctx->ev1));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::GEMM_SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
   load_driver_entry_points();
   ctx->ready = true;
   return ctx;
@@ -132,6 +135,9 @@ extern "C" void phpc_b200_finalize(void) {
     if (ctx->bufA.ptr) cudaFree(ctx->bufA.ptr);
     if (ctx->bufB.ptr) cudaFree(ctx->bufB.ptr);
     if (ctx->bufC.ptr) cudaFree(ctx->bufC.ptr);
+    if (ctx->ozA.ptr) cudaFree(ctx->ozA.ptr);
+    if (ctx->ozB.ptr) cudaFree(ctx->ozB.ptr);
+    if (ctx->ozE.ptr) cudaFree(ctx->ozE.ptr);
     cudaFree(ctx->sched);
     cublasDestroy(ctx->blas);
     cudaEventDestroy(ctx->ev0);
@@ -241,6 +247,85 @@ int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const doub
   return 1;
 }
 
+/* ------------------------------------------------------------------------- */
+/* Ozaki (int8 tcgen05) launcher                                              */
+/* ------------------------------------------------------------------------- */
+static void encode_map_bytes(CUtensorMap *map, const void *base, long long inner_bytes, long long outer, int box_inner, int box_outer) {
+  cuuint64_t gdim[2] = {(cuuint64_t)inner_bytes, (cuuint64_t)outer};
+  cuuint64_t gstride[1] = {(cuuint64_t)inner_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "CUresult %d (digit matrix %lld x %lld bytes)", (int)r, outer, inner_bytes);
+    phpc_die("cuTensorMapEncodeTiled", msg, __FILE__, __LINE__);
+  }
+}
+
+int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
+                      int k, int n, int slices, cudaStream_t stream) {
+  using namespace phpc::oz;
+  if (m <= 0 || n <= 0 || k <= 0) return 0;
+  PHPC_REQUIRE(lda >= k && ldb >= n && ldc >= n, "leading dimension smaller than the row length");
+  if (slices <= 0) {
+    const char *e = getenv("PHPC_OZAKI_SLICES");
+    slices = (e && *e) ? atoi(e) : 8;
+  }
+  PHPC_REQUIRE(slices >= 2 && slices <= MAX_SLICES, "PHPC_OZAKI_SLICES must be in 2..8");
+  /* int32 accumulation of a whole group is exact while  K * S * 127^2 < 2^31  (S = 8: K <= 16643) */
+  const int kc_max = 8192;
+  int launches = 0;
+  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+  const long long tiles = (long long)tiles_m * tiles_n;
+  PHPC_REQUIRE(tiles < (1ll << 30) && (long long)slices * m < (1ll << 31) && (long long)slices * n < (1ll << 31), "problem too large");
+  for (int k0 = 0; k0 < k; k0 += kc_max) {
+    const int kc = (k - k0 < kc_max) ? k - k0 : kc_max;
+    const int kp = (kc + BKB - 1) / BKB * BKB;
+    int8_t *SA = (int8_t *)phpc_buf_reserve(&ctx->ozA, (size_t)slices * m * kp);
+    int8_t *SB = (int8_t *)phpc_buf_reserve(&ctx->ozB, (size_t)slices * n * kp);
+    int *eA = (int *)phpc_buf_reserve(&ctx->ozE, ((size_t)m + n) * sizeof(int));
+    int *eB = eA + m;
+    const double *a = dA + k0;
+    const double *b = dB + (long long)k0 * ldb;
+    exp_init_kernel<<<(m + n + 255) / 256, 256, 0, stream>>>(eA, m + n);
+    {
+      const int segs = (kc + 1023) / 1024;
+      const long long units = (long long)m * segs;
+      row_exp_kernel<<<(unsigned)((units + 7) / 8), 256, 0, stream>>>(a, lda, m, kc, eA);
+      dim3 grid((n + 255) / 256, (kc + 63) / 64);
+      col_exp_kernel<<<grid, 256, 0, stream>>>(b, ldb, kc, n, eB);
+    }
+    {
+      const long long threads = (long long)m * (kp / 16);
+      split_a_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, SA, slices);
+      dim3 grid((n + 127) / 128, kp / 32);
+      split_b_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, SB, slices);
+    }
+    CUtensorMap tmA, tmB;
+    encode_map_bytes(&tmA, SA, kp, (long long)slices * m, BKB, BM);
+    encode_map_bytes(&tmB, SB, kp, (long long)slices * n, BKB, BN);
+    Params p;
+    p.C = dC;
+    p.ldc = ldc;
+    p.M = m;
+    p.N = n;
+    p.kblocks = kp / BKB;
+    p.S = slices;
+    p.eA = eA;
+    p.eB = eB;
+    p.tiles_m = tiles_m;
+    p.tiles_n = tiles_n;
+    int grid = ctx->sm_count;
+    if ((long long)grid > tiles) grid = (int)tiles;
+    ozaki_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+    CUDA_CHECK(cudaGetLastError());
+    launches += 6;
+  }
+  return launches;
+}
+
 void phpc_launch_cublas(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                         int k, int n, cudaStream_t stream) {
   if (m <= 0 || n <= 0 || k <= 0) return;
@@ -262,14 +347,22 @@ extern "C" void phpc_gemm_device_cublas(const double *dA, long long lda, const d
   phpc_launch_cublas(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, stream ? (cudaStream_t)stream : ctx->compute);
 }
 
+extern "C" int phpc_gemm_device_ozaki(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
+                                      int k, int n, int slices, void *stream) {
+  DeviceCtx *ctx = phpc_cur_ctx();
+  return phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, slices, stream ? (cudaStream_t)stream : ctx->compute);
+}
+
 extern "C" float phpc_gemm_device_timed(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                                         int k, int n, int ctas, int reps, int use_cublas) {
   DeviceCtx *ctx = phpc_cur_ctx();
   if (reps < 1) reps = 1;
   CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->compute));
   for (int r = 0; r < reps; ++r) {
-    if (use_cublas)
+    if (use_cublas == 1)
       phpc_launch_cublas(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctx->compute);
+    else if (use_cublas == 2)
+      phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, 0, ctx->compute);
     else
       phpc_launch_dmma(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctas, ctx->compute);
   }

@@ -51,6 +51,7 @@ struct DeviceCtx {
   unsigned int *sched = nullptr; /* tile-scheduler words, self-resetting */
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf bufA, bufB, bufC;
+  DevBuf ozA, ozB, ozE; /* Ozaki digit matrices of the current K chunk and the row/column exponents */
 };
 
 DeviceCtx *phpc_ctx(int device); /* lazily created; makes `device` current */
@@ -60,6 +61,10 @@ void *phpc_buf_reserve(DevBuf *b, size_t bytes);
 /* enqueue the DMMA kernel on `stream`; returns launches (0 or 1) */
 int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                      int k, int n, int ctas, cudaStream_t stream);
+/* FP64 GEMM rebuilt from int8 tcgen05 MMAs (Ozaki scheme, `slices` 7-bit digits per operand,
+ * <= 0 picks PHPC_OZAKI_SLICES or 8); returns the number of kernels launched */
+int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
+                      int k, int n, int slices, cudaStream_t stream);
 void phpc_launch_cublas(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                         int k, int n, cudaStream_t stream);
 

@@ -600,6 +600,8 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
     if (backend == PHPC_BACKEND_CUBLAS) {
       phpc_launch_cublas(ctx, a, lda, b, s->ldn, s->dC, s->ldn, s->m, st.width, s->n, comp);
       ++launches;
+    } else if (backend == PHPC_BACKEND_OZAKI) {
+      launches += phpc_launch_ozaki(ctx, a, lda, b, s->ldn, s->dC, s->ldn, s->m, st.width, s->n, 0, comp);
     } else {
       int use = ctas;
       if (any_comm && !pull && comm_sms > 0 && q + 1 < nsteps) {

@@ -60,10 +60,19 @@ int phpc_gemm_device(const double *dA, long long lda, const double *dB, long lon
 /* Same contraction through cublasDgemm (alpha = beta = 1) on the same stream. */
 void phpc_gemm_device_cublas(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m, int k,
                              int n, void *stream);
+/*
+ * Same contraction on the tcgen05 tensor cores: A and B are cut into `slices` signed 7-bit
+ * digit matrices (error-free, per-row / per-column power-of-two scaling), the digit products run
+ * as int8 MMAs with exact int32 accumulators in TMEM, and the FP64 result is reassembled in the
+ * epilogue (Ozaki scheme; slices <= 0 = PHPC_OZAKI_SLICES or 8, i.e. 56 bits below each row /
+ * column maximum).  Inputs must be finite.  Returns the number of kernels launched.
+ */
+int phpc_gemm_device_ozaki(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m, int k,
+                           int n, int slices, void *stream);
 /* Run phpc_gemm_device `reps` times back to back and return the mean device
  * milliseconds per launch (CUDA events on the launching stream). */
 float phpc_gemm_device_timed(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m, int k,
-                             int n, int ctas, int reps, int use_cublas);
+                             int n, int ctas, int reps, int backend /* 0 DMMA, 1 cuBLAS, 2 Ozaki */);
 
 /* ---- synthetic inputs (device side) --------------------------------------- */
 /*

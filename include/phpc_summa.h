@@ -39,6 +39,7 @@ void phpc_gemm_summa_cublas(MPI_Comm grid_comm, const double *A, const double *B
 
 #define PHPC_BACKEND_DMMA 0
 #define PHPC_BACKEND_CUBLAS 1
+#define PHPC_BACKEND_OZAKI 2 /* FP64 rebuilt from int8 tcgen05 MMAs, see phpc_gemm_device_ozaki */
 
 /* One k-step of the schedule as rank (pi, pj) sees it. */
 typedef struct phpc_summa_step {
