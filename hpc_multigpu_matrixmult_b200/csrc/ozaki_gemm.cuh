@@ -41,7 +41,8 @@ constexpr int A_BYTES = BM * BKB;
 constexpr int B_BYTES = BN * BKB;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int THREADS = 192; /* warp 0 TMA, warp 1 MMA, warps 2-5 epilogue */
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int EPI_WARP_BYTES = 32 * 33 * 4; /* per epilogue warp: 32 x 32 int32 transpose tile, padded */
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * EPI_WARP_BYTES;
 constexpr int TMEM_COLS = 512; /* two int32 accumulators of 256 columns */
 constexpr int DIGIT_BITS = 7;
 constexpr int MAX_SLICES = 8;
@@ -98,6 +99,18 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, int (&v)[16])
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, int (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+        "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
 /* 2^e as a double (e clamped to the normal range; INT_MIN exponents mean "all zero") */
 __device__ __forceinline__ double pow2d(int e) {
   e = max(-1022, min(1023, e));
@@ -112,6 +125,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES;
   const uint32_t tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
   const uint32_t tmem_slot = tempty0 + 16; /* 4 bytes: TMEM base address written by tcgen05.alloc */
+  const uint32_t epi0 = bars + 256;        /* transpose tiles of the epilogue warps */
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -208,38 +222,46 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   } else {
-    /* ===== epilogue: 4 warps, warp w reads TMEM lanes 32*(w%4) .. +31 ===== */
+    /* ===== epilogue: 4 warps, warp w reads TMEM lanes 32*(w%4) .. +31 =====
+     * tcgen05.ld hands every thread one ROW of the accumulator; a 32x32 int32 block is turned
+     * through shared memory so that the C read-modify-write is done with lanes along a row
+     * (256 contiguous bytes per warp access). */
     const int quarter = warp & 3;
+    const uint32_t tr = epi0 + (uint32_t)(warp - 2) * EPI_WARP_BYTES; /* this warp's 32 x 33 int32 transpose tile */
     uint32_t unit = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int tm, tn;
       tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-      const int row = tm * BM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const int ea = row_ok ? p.eA[row] : ZERO_EXP;
-      double *crow = p.C + (long long)(row_ok ? row : 0) * p.ldc;
+      const int row0 = tm * BM + quarter * 32;
+      const int my_row = row0 + lane;
+      const int ea = (my_row < p.M) ? p.eA[my_row] : ZERO_EXP; /* lane r holds the exponent of row row0 + r */
+      const int rows_here = min(32, p.M - row0);               /* <= 0: nothing of this warp's rows is inside C */
       for (int g = S + 1; g >= 2; --g, ++unit) {
         const uint32_t buf = unit & 1;
         mbar_wait(tfull0 + 8 * buf, (unit >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
-        const int erow = ea - DIGIT_BITS * g;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          int v[16];
-          tmem_ld_32x32b_x16(taddr + c0, v);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int col = tn * BN + c0 + lane; /* the column this lane owns after the transpose */
+          if (tn * BN + c0 >= p.N || rows_here <= 0) break;
+          int v[32];
+          tmem_ld_32x32b_x32(taddr + c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          const int col0 = tn * BN + c0;
-          if (row_ok && ea != ZERO_EXP && col0 < p.N) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int col = col0 + j;
-              if (col < p.N) {
-                const int eb = __ldg(p.eB + col);
-                if (eb != ZERO_EXP && v[j] != 0) crow[col] += (double)v[j] * pow2d(erow + eb); /* exact product, one rounding */
-              }
-            }
+          for (int j = 0; j < 32; ++j) asm volatile("st.shared.b32 [%0], %1;" ::"r"(tr + (uint32_t)(lane * 33 + j) * 4), "r"(v[j]) : "memory");
+          __syncwarp();
+          const int eb = (col < p.N) ? __ldg(p.eB + col) : ZERO_EXP;
+          double *cptr = p.C + (long long)row0 * p.ldc + col;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            int x;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x) : "r"(tr + (uint32_t)(rr * 33 + lane) * 4) : "memory");
+            const int er = __shfl_sync(0xffffffffu, ea, rr);
+            if (rr < rows_here && eb != ZERO_EXP && er != ZERO_EXP && x != 0)
+              cptr[(long long)rr * p.ldc] += (double)x * pow2d(er + eb - DIGIT_BITS * g); /* exact product, one rounding */
           }
+          __syncwarp();
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -257,4 +279,226 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 }  // namespace oz
+}  // namespace phpc
+
+/* =====================================================================================
+ * Version 2: K-outer schedule.  v1 walks the pairs (t,u) in the outer loop and streams a
+ * fresh A_t and B_u tile for every MMA group, i.e. 96 bytes of operands per SM-cycle of tensor
+ * work — ncu shows it memory-system bound (profiles/ncu_ozaki_gemm_n8192_r01_v1.txt).
+ * v2 turns the loops around: per 32-byte k step ALL needed digit tiles of A and B are staged
+ * once (one 4 KiB slot per digit matrix, 32-byte swizzle) and every pair (t,u) of up to four
+ * groups is issued from them, with one TMEM accumulator (128 columns) per group:
+ *   pass 1  groups S+1 .. S-2   (the 4 least significant; needs every digit)
+ *   pass 2  groups S-3 .. 2     (digits 1..S-4 only)
+ * Operand traffic drops to ~40 bytes per SM-cycle, and the epilogue combines the four groups of
+ * a pass exactly in FP64 (<= 52 significant bits) before ONE read-modify-write of C.
+ * ===================================================================================== */
+namespace phpc {
+namespace oz2 {
+
+using oz::DIGIT_BITS;
+using oz::ZERO_EXP;
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BKB = 32;                /* bytes of k per stage = one int8 MMA (K = 32) */
+constexpr int SLOT_BYTES = BM * BKB;   /* one digit tile: 128 rows x 32 B */
+constexpr int MAX_S = 8;
+constexpr int STAGE_BYTES = 2 * MAX_S * SLOT_BYTES; /* A digits then B digits */
+constexpr int STAGES = 3;
+constexpr int THREADS = 192;
+constexpr int EPI_WARP_BYTES = 32 * 33 * 8; /* 32 x 32 doubles, padded */
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * EPI_WARP_BYTES;
+constexpr int GROUPS_PER_PASS = 4;
+constexpr int TMEM_COLS = GROUPS_PER_PASS * BN; /* 512 */
+
+struct Params {
+  double *C;
+  long long ldc;
+  int M, N;
+  int ksteps; /* padded K / 32 */
+  int S;
+  const int *eA;
+  const int *eB;
+  int tiles_m, tiles_n;
+};
+
+/* K-major, 32-byte swizzle: 8-row atoms of 256 bytes */
+__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61; /* SWIZZLE_32B */
+  return d;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+    ozaki_gemm_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES;
+  const uint32_t tfull = bars + 16 * STAGES, tempty = tfull + 8;
+  const uint32_t tmem_slot = tempty + 8;
+  const uint32_t epi0 = bars + 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int S = p.S;
+  const int npass = (S + GROUPS_PER_PASS - 1) / GROUPS_PER_PASS; /* S groups (g = 2 .. S+1) */
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    /* ===== TMA producer: per k step, one 4 KiB tile per needed digit matrix of A and of B ===== */
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int tm, tn;
+        tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+        for (int ps = 0; ps < npass; ++ps) {
+          const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
+          const int d_hi = min(S, g_hi - 1); /* digits 1 .. d_hi take part in this pass */
+          for (int ks = 0; ks < p.ksteps; ++ks) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t full = full0 + 8 * stage;
+            mbar_expect_tx(full, 2 * d_hi * SLOT_BYTES);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            for (int t = 1; t <= d_hi; ++t) {
+              tma_load_2d(sa + (t - 1) * SLOT_BYTES, &tmA, full, ks * BKB, (t - 1) * p.M + tm * BM);
+              tma_load_2d(sa + (MAX_S + t - 1) * SLOT_BYTES, &tmB, full, ks * BKB, (t - 1) * p.N + tn * BN);
+            }
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    /* ===== MMA issuer ===== */
+    if (lane == 0) {
+      const uint32_t idesc = oz::idesc_i8(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t unit = 0; /* (tile, pass) counter */
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int ps = 0; ps < npass; ++ps, ++unit) {
+          const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
+          const int g_lo = max(2, g_hi - GROUPS_PER_PASS + 1);
+          mbar_wait(tempty, (unit & 1) ^ 1); /* epilogue drained the accumulators of the previous pass */
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int ks = 0; ks < p.ksteps; ++ks) {
+            mbar_wait(full0 + 8 * stage, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            for (int g = g_hi; g >= g_lo; --g) {
+              const uint32_t tacc = tmem_base + (uint32_t)(g - g_lo) * BN;
+              const int t_lo = max(1, g - S), t_hi = min(S, g - 1);
+              for (int t = t_lo; t <= t_hi; ++t) {
+                const int u = g - t;
+                oz::umma_i8(tacc, smem_desc_sw32(sa + (t - 1) * SLOT_BYTES), smem_desc_sw32(sa + (MAX_S + u - 1) * SLOT_BYTES), idesc,
+                            (ks > 0 || t > t_lo) ? 1u : 0u);
+              }
+            }
+            oz::umma_commit(empty0 + 8 * stage);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          oz::umma_commit(tfull);
+        }
+      }
+    }
+  } else {
+    /* ===== epilogue: combine the groups of a pass exactly, then one C += per element ===== */
+    const int quarter = warp & 3;
+    const uint32_t tr = epi0 + (uint32_t)(warp - 2) * EPI_WARP_BYTES;
+    uint32_t unit = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int tm, tn;
+      tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+      const int row0 = tm * BM + quarter * 32;
+      const int my_row = row0 + lane;
+      const int ea = (my_row < p.M) ? p.eA[my_row] : ZERO_EXP;
+      const int rows_here = min(32, p.M - row0);
+      for (int ps = 0; ps < npass; ++ps, ++unit) {
+        const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
+        const int g_lo = max(2, g_hi - GROUPS_PER_PASS + 1);
+        mbar_wait(tfull, unit & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (tn * BN + c0 >= p.N || rows_here <= 0) break;
+          double acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+          for (int g = g_hi; g >= g_lo; --g) { /* least significant group first; every partial sum is exact */
+            int v[32];
+            oz::tmem_ld_32x32b_x32(tlane + (uint32_t)(g - g_lo) * BN + c0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const double w = oz::pow2d(DIGIT_BITS * (g_hi - g)); /* relative weight inside the pass: 2^(7(g_hi-g)) */
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(tr + (uint32_t)(lane * 33 + j) * 8), "d"(acc[j]) : "memory");
+          __syncwarp();
+          const int col = tn * BN + c0 + lane;
+          const int eb = (col < p.N) ? __ldg(p.eB + col) : ZERO_EXP;
+          double *cptr = p.C + (long long)row0 * p.ldc + col;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            double x;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(tr + (uint32_t)(rr * 33 + lane) * 8) : "memory");
+            const int er = __shfl_sync(0xffffffffu, ea, rr);
+            if (rr < rows_here && eb != ZERO_EXP && er != ZERO_EXP && x != 0.0)
+              cptr[(long long)rr * p.ldc] += x * oz::pow2d(er + eb - DIGIT_BITS * g_hi);
+          }
+          __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace oz2
 }  // namespace phpc

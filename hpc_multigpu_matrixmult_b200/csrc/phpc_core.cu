@@ -86,6 +86,7 @@ DeviceCtx *phpc_ctx(int device) {
   CUDA_CHECK(cudaEventCreate(&ctx->ev1));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::GEMM_SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz2::ozaki_gemm_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz2::SMEM_BYTES));
   load_driver_entry_points();
   ctx->ready = true;
   return ctx;
@@ -250,13 +251,14 @@ int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const doub
 /* ------------------------------------------------------------------------- */
 /* Ozaki (int8 tcgen05) launcher                                              */
 /* ------------------------------------------------------------------------- */
-static void encode_map_bytes(CUtensorMap *map, const void *base, long long inner_bytes, long long outer, int box_inner, int box_outer) {
+static void encode_map_bytes(CUtensorMap *map, const void *base, long long inner_bytes, long long outer, int box_inner, int box_outer,
+                             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t gdim[2] = {(cuuint64_t)inner_bytes, (cuuint64_t)outer};
   cuuint64_t gstride[1] = {(cuuint64_t)inner_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estride[2] = {1, 1};
   CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                              swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[160];
     snprintf(msg, sizeof msg, "CUresult %d (digit matrix %lld x %lld bytes)", (int)r, outer, inner_bytes);
@@ -277,7 +279,10 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
   /* int32 accumulation of a whole group is exact while  K * S * 127^2 < 2^31  (S = 8: K <= 16643) */
   const int kc_max = 8192;
   int launches = 0;
-  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
+  const char *kv = getenv("PHPC_OZAKI_KERNEL");
+  const int version = (kv && *kv) ? atoi(kv) : 2; /* 1 = pair-outer 128x256 tiles, 2 = K-outer 128x128 tiles */
+  const int bn = version == 1 ? BN : phpc::oz2::BN;
+  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + bn - 1) / bn;
   const long long tiles = (long long)tiles_m * tiles_n;
   PHPC_REQUIRE(tiles < (1ll << 30) && (long long)slices * m < (1ll << 31) && (long long)slices * n < (1ll << 31), "problem too large");
   for (int k0 = 0; k0 < k; k0 += kc_max) {
@@ -304,22 +309,40 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
       split_b_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, SB, slices);
     }
     CUtensorMap tmA, tmB;
-    encode_map_bytes(&tmA, SA, kp, (long long)slices * m, BKB, BM);
-    encode_map_bytes(&tmB, SB, kp, (long long)slices * n, BKB, BN);
-    Params p;
-    p.C = dC;
-    p.ldc = ldc;
-    p.M = m;
-    p.N = n;
-    p.kblocks = kp / BKB;
-    p.S = slices;
-    p.eA = eA;
-    p.eB = eB;
-    p.tiles_m = tiles_m;
-    p.tiles_n = tiles_n;
     int grid = ctx->sm_count;
     if ((long long)grid > tiles) grid = (int)tiles;
-    ozaki_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+    if (version == 1) {
+      encode_map_bytes(&tmA, SA, kp, (long long)slices * m, BKB, BM);
+      encode_map_bytes(&tmB, SB, kp, (long long)slices * n, BKB, BN);
+      Params p;
+      p.C = dC;
+      p.ldc = ldc;
+      p.M = m;
+      p.N = n;
+      p.kblocks = kp / BKB;
+      p.S = slices;
+      p.eA = eA;
+      p.eB = eB;
+      p.tiles_m = tiles_m;
+      p.tiles_n = tiles_n;
+      ozaki_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
+    } else {
+      namespace v2 = phpc::oz2;
+      encode_map_bytes(&tmA, SA, kp, (long long)slices * m, v2::BKB, v2::BM, CU_TENSOR_MAP_SWIZZLE_32B);
+      encode_map_bytes(&tmB, SB, kp, (long long)slices * n, v2::BKB, v2::BN, CU_TENSOR_MAP_SWIZZLE_32B);
+      v2::Params p;
+      p.C = dC;
+      p.ldc = ldc;
+      p.M = m;
+      p.N = n;
+      p.ksteps = kp / v2::BKB;
+      p.S = slices;
+      p.eA = eA;
+      p.eB = eB;
+      p.tiles_m = tiles_m;
+      p.tiles_n = tiles_n;
+      v2::ozaki_gemm_kernel_v2<<<grid, v2::THREADS, v2::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    }
     CUDA_CHECK(cudaGetLastError());
     launches += 6;
   }

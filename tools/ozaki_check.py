@@ -45,6 +45,37 @@ def main():
         for s in (4, 6, 7, 8):
             rel, exact, _, _ = one(L, 512, 2048, 512, 1, s)
             print(json.dumps({"slices": s, "rel_vs_dmma": rel}), flush=True)
+    elif mode == "sustain":
+        import subprocess
+        import threading
+        import time
+        n = int(sys.argv[2])
+        secs = float(sys.argv[3]) if len(sys.argv) > 3 else 3.0
+        m = k = n
+        dA, dB, dC = (L.phpc_device_malloc(n * n * 8) for _ in range(3))
+        L.phpc_fill_device(dA, n, m, k, 0, 0, k, 1, 11, None)
+        L.phpc_fill_device(dB, n, k, n, 0, 0, n, 1, 22, None)
+        L.phpc_device_memset(dC, 0, n * n * 8)
+        for name, be in (("dmma", 0), ("ozaki", 2)):
+            ms1 = L.phpc_gemm_device_timed(dA, n, dB, n, dC, n, m, k, n, 0, 1, be)
+            reps = max(2, int(secs * 1000 / ms1))
+            samples = []
+            stop = threading.Event()
+
+            def poll():
+                while not stop.is_set():
+                    out = subprocess.run(["nvidia-smi", "-i", "0", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout.strip()
+                    samples.append(out)
+                    time.sleep(0.2)
+
+            th = threading.Thread(target=poll)
+            th.start()
+            ms = L.phpc_gemm_device_timed(dA, n, dB, n, dC, n, m, k, n, 0, reps, be)
+            stop.set()
+            th.join()
+            print(json.dumps({"n": n, "backend": name, "burst_tflops": round(2.0 * n ** 3 / ms1 / 1e9, 2), "sustained_tflops": round(2.0 * n ** 3 / ms / 1e9, 2),
+                              "reps": reps, "clock_power_samples": samples[1:-1][:12]}), flush=True)
     else:
         for a in sys.argv[2:] or ["4096", "8192", "16384"]:
             m = k = n = int(a)
