@@ -502,3 +502,227 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 }  // namespace oz2
 }  // namespace phpc
+
+/* =====================================================================================
+ * Version 3: v2's K-outer schedule fed by 1-D bulk copies.  ncu on v2 shows the tensor pipe only
+ * 43 % busy with DRAM and L2 far from saturated (profiles/ncu_ozaki_gemm_n8192_r01_v2.txt): a
+ * k step needs 16 TMA boxes of 128 rows x 32 B, i.e. 2048 separate 32-byte rows, and the TMA
+ * row rate, not bandwidth, paces the pipeline.  The split kernels therefore emit the digits
+ * ALREADY in the shared-memory order the tensor core wants (UMMA canonical K-major, no swizzle:
+ * 8-row x 16-byte core matrices; 128-row x 32-byte tile = 4 KiB, k chunks 128 B apart, 8-row groups
+ * 256 B apart), tile after tile:
+ *     store[row tile][k step][digit][4 KiB tile]
+ * so one k step of a pass is ONE contiguous global range per operand (digits 1..d are the first
+ * d tiles) and the producer issues two cp.async.bulk copies instead of 16 tensor copies.
+ * ===================================================================================== */
+namespace phpc {
+namespace oz3 {
+
+using oz::DIGIT_BITS;
+using oz::ZERO_EXP;
+/* same tile shape, stages and TMEM use as v2 */
+constexpr int BM = oz2::BM, BN = oz2::BN, SLOT_BYTES = oz2::SLOT_BYTES, MAX_S = oz2::MAX_S, STAGE_BYTES = oz2::STAGE_BYTES;
+constexpr int STAGES = oz2::STAGES, THREADS = oz2::THREADS, EPI_WARP_BYTES = oz2::EPI_WARP_BYTES, SMEM_BYTES = oz2::SMEM_BYTES;
+constexpr int GROUPS_PER_PASS = oz2::GROUPS_PER_PASS, TMEM_COLS = oz2::TMEM_COLS;
+
+constexpr int TILE_BYTES = SLOT_BYTES; /* 4096 */
+
+struct Params3 {
+  double *C;
+  long long ldc;
+  int M, N;
+  int ksteps;
+  int S;
+  const int *eA;
+  const int *eB;
+  int tiles_m, tiles_n;
+  const int8_t *TA; /* [tiles_m][ksteps][S][4096] */
+  const int8_t *TB; /* [tiles_n][ksteps][S][4096] */
+};
+
+/* byte offset of element (row r < 128, k byte kb < 32) inside a canonical 4 KiB tile */
+__host__ __device__ __forceinline__ int tile_offset(int r, int kb) { return (r >> 3) * 256 + (kb >> 4) * 128 + (r & 7) * 16 + (kb & 15); }
+
+/* UMMA descriptor, K-major, no swizzle: LBO = 128 B between the two k chunks, SBO = 256 B between 8-row groups */
+__device__ __forceinline__ uint64_t smem_desc_kmajor_noswz(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(128 >> 4) << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3 p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES;
+  const uint32_t tfull = bars + 16 * STAGES, tempty = tfull + 8;
+  const uint32_t tmem_slot = tempty + 8;
+  const uint32_t epi0 = bars + 256;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+  const int S = p.S;
+  const int npass = (S + GROUPS_PER_PASS - 1) / GROUPS_PER_PASS;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    /* ===== producer: two contiguous bulk copies per k step ===== */
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const size_t step_bytes = (size_t)S * TILE_BYTES;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int tm, tn;
+        tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+        const int8_t *ta = p.TA + (size_t)tm * p.ksteps * step_bytes;
+        const int8_t *tb = p.TB + (size_t)tn * p.ksteps * step_bytes;
+        for (int ps = 0; ps < npass; ++ps) {
+          const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
+          const uint32_t bytes = (uint32_t)min(S, g_hi - 1) * TILE_BYTES; /* digits 1 .. d_hi */
+          for (int ks = 0; ks < p.ksteps; ++ks) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            const uint32_t full = full0 + 8 * stage;
+            mbar_expect_tx(full, 2 * bytes);
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            bulk_load(sa, ta + (size_t)ks * step_bytes, bytes, full);
+            bulk_load(sa + MAX_S * SLOT_BYTES, tb + (size_t)ks * step_bytes, bytes, full);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    /* ===== MMA issuer ===== */
+    if (lane == 0) {
+      const uint32_t idesc = oz::idesc_i8(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t unit = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int ps = 0; ps < npass; ++ps, ++unit) {
+          const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
+          const int g_lo = max(2, g_hi - GROUPS_PER_PASS + 1);
+          mbar_wait(tempty, (unit & 1) ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int ks = 0; ks < p.ksteps; ++ks) {
+            mbar_wait(full0 + 8 * stage, phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem_base + stage * STAGE_BYTES;
+            const uint64_t da0 = smem_desc_kmajor_noswz(sa), db0 = smem_desc_kmajor_noswz(sa + MAX_S * SLOT_BYTES);
+            for (int g = g_hi; g >= g_lo; --g) {
+              const uint32_t tacc = tmem_base + (uint32_t)(g - g_lo) * BN;
+              const int t_lo = max(1, g - S), t_hi = min(S, g - 1);
+              for (int t = t_lo; t <= t_hi; ++t) {
+                const int u = g - t;
+                oz::umma_i8(tacc, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)), db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc,
+                            (ks > 0 || t > t_lo) ? 1u : 0u);
+              }
+            }
+            oz::umma_commit(empty0 + 8 * stage);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          oz::umma_commit(tfull);
+        }
+      }
+    }
+  } else {
+    /* ===== epilogue (as v2) ===== */
+    const int quarter = warp & 3;
+    const uint32_t tr = epi0 + (uint32_t)(warp - 2) * EPI_WARP_BYTES;
+    uint32_t unit = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int tm, tn;
+      tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+      const int row0 = tm * BM + quarter * 32;
+      const int my_row = row0 + lane;
+      const int ea = (my_row < p.M) ? p.eA[my_row] : ZERO_EXP;
+      const int rows_here = min(32, p.M - row0);
+      for (int ps = 0; ps < npass; ++ps, ++unit) {
+        const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
+        const int g_lo = max(2, g_hi - GROUPS_PER_PASS + 1);
+        mbar_wait(tfull, unit & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (tn * BN + c0 >= p.N || rows_here <= 0) break;
+          double acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+          for (int g = g_hi; g >= g_lo; --g) {
+            int v[32];
+            oz::tmem_ld_32x32b_x32(tlane + (uint32_t)(g - g_lo) * BN + c0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const double w = oz::pow2d(DIGIT_BITS * (g_hi - g));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(tr + (uint32_t)(lane * 33 + j) * 8), "d"(acc[j]) : "memory");
+          __syncwarp();
+          const int col = tn * BN + c0 + lane;
+          const int eb = (col < p.N) ? __ldg(p.eB + col) : ZERO_EXP;
+          double *cptr = p.C + (long long)row0 * p.ldc + col;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            double x;
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(tr + (uint32_t)(rr * 33 + lane) * 8) : "memory");
+            const int er = __shfl_sync(0xffffffffu, ea, rr);
+            if (rr < rows_here && eb != ZERO_EXP && er != ZERO_EXP && x != 0.0)
+              cptr[(long long)rr * p.ldc] += x * oz::pow2d(er + eb - DIGIT_BITS * g_hi);
+          }
+          __syncwarp();
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace oz3
+}  // namespace phpc

@@ -127,3 +127,80 @@ __global__ void split_b_kernel(const double *__restrict__ B, long long ldb, int 
 
 }  // namespace oz
 }  // namespace phpc
+
+/* ---- tiled digit stores for ozaki_gemm_kernel_v3: store[row tile][k step][digit][4 KiB canonical tile] ---- */
+namespace phpc {
+namespace oz3 {
+
+/* A: thread = 16 consecutive k of one (padded) row = one 16-byte chunk of a core matrix per digit */
+__global__ void split_a_tiled_kernel(const double *__restrict__ A, long long lda, int m, int k, int kp, const int *__restrict__ eA,
+                                     int8_t *__restrict__ TA, int S) {
+  const int chunks = kp / 16;
+  const int m_pad = (m + 127) / 128 * 128;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)m_pad * chunks) return;
+  /* consecutive threads walk down the rows of one k chunk: the 8 rows of a core matrix are 128 contiguous bytes */
+  const int chunk = (int)(idx / m_pad), row = (int)(idx % m_pad);
+  const int c0 = chunk * 16;
+  const int e = row < m ? eA[row] : oz::ZERO_EXP;
+  double r[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int c = c0 + j;
+    r[j] = (row < m && c < k && e != oz::ZERO_EXP) ? scalbn(A[(long long)row * lda + c], -e) : 0.0;
+  }
+  const int ksteps = kp / 32;
+  const size_t base = (((size_t)(row >> 7) * ksteps + (c0 >> 5)) * S) * 4096 + tile_offset(row & 127, c0 & 31);
+  for (int t = 0; t < S; ++t) {
+    union {
+      int8_t b[16];
+      int4 v;
+    } out;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const double s = r[j] * 128.0;
+      const int d = (int)s;
+      r[j] = s - (double)d;
+      out.b[j] = (int8_t)d;
+    }
+    *reinterpret_cast<int4 *>(TA + base + (size_t)t * 4096) = out.v;
+  }
+}
+
+/* B (transposed): thread = 32 consecutive k of one (padded) column; warp = 32 adjacent columns */
+__global__ void split_b_tiled_kernel(const double *__restrict__ B, long long ldb, int k, int n, int kp, const int *__restrict__ eB,
+                                     int8_t *__restrict__ TB, int S) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_pad = (n + 127) / 128 * 128;
+  if (col >= n_pad) return;
+  const int ks = blockIdx.y; /* k step of 32 */
+  const int k0 = ks * 32;
+  const int e = col < n ? eB[col] : oz::ZERO_EXP;
+  double r[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int row = k0 + j;
+    r[j] = (col < n && row < k && e != oz::ZERO_EXP) ? scalbn(B[(long long)row * ldb + col], -e) : 0.0;
+  }
+  const int ksteps = kp / 32;
+  const size_t base = (((size_t)(col >> 7) * ksteps + ks) * S) * 4096 + tile_offset(col & 127, 0);
+  for (int t = 0; t < S; ++t) {
+    union {
+      int8_t b[32];
+      int4 v[2];
+    } out;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const double s = r[j] * 128.0;
+      const int d = (int)s;
+      r[j] = s - (double)d;
+      out.b[j] = (int8_t)d;
+    }
+    int8_t *dst = TB + base + (size_t)t * 4096;
+    *reinterpret_cast<int4 *>(dst) = out.v[0];       /* k bytes 0..15  */
+    *reinterpret_cast<int4 *>(dst + 128) = out.v[1]; /* k bytes 16..31: next core matrix along k */
+  }
+}
+
+}  // namespace oz3
+}  // namespace phpc

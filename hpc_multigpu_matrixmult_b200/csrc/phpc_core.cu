@@ -87,6 +87,7 @@ DeviceCtx *phpc_ctx(int device) {
   CUDA_CHECK(cudaFuncSetAttribute(phpc::dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::GEMM_SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz2::ozaki_gemm_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz2::SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz3::ozaki_gemm_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz2::SMEM_BYTES));
   load_driver_entry_points();
   ctx->ready = true;
   return ctx;
@@ -280,7 +281,7 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
   const int kc_max = 8192;
   int launches = 0;
   const char *kv = getenv("PHPC_OZAKI_KERNEL");
-  const int version = (kv && *kv) ? atoi(kv) : 2; /* 1 = pair-outer 128x256 tiles, 2 = K-outer 128x128 tiles */
+  const int version = (kv && *kv) ? atoi(kv) : 3; /* 1 = pair-outer 128x256 tiles (TMA), 2 = K-outer 128x128 (TMA), 3 = K-outer, pre-tiled + bulk copies */
   const int bn = version == 1 ? BN : phpc::oz2::BN;
   const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + bn - 1) / bn;
   const long long tiles = (long long)tiles_m * tiles_n;
@@ -288,8 +289,9 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
   for (int k0 = 0; k0 < k; k0 += kc_max) {
     const int kc = (k - k0 < kc_max) ? k - k0 : kc_max;
     const int kp = (kc + BKB - 1) / BKB * BKB;
-    int8_t *SA = (int8_t *)phpc_buf_reserve(&ctx->ozA, (size_t)slices * m * kp);
-    int8_t *SB = (int8_t *)phpc_buf_reserve(&ctx->ozB, (size_t)slices * n * kp);
+    const size_t m_pad = (size_t)tiles_m * BM, n_pad = (size_t)tiles_n * bn;
+    int8_t *SA = (int8_t *)phpc_buf_reserve(&ctx->ozA, (size_t)slices * (version == 3 ? m_pad : (size_t)m) * kp);
+    int8_t *SB = (int8_t *)phpc_buf_reserve(&ctx->ozB, (size_t)slices * (version == 3 ? n_pad : (size_t)n) * kp);
     int *eA = (int *)phpc_buf_reserve(&ctx->ozE, ((size_t)m + n) * sizeof(int));
     int *eB = eA + m;
     const double *a = dA + k0;
@@ -302,7 +304,12 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
       dim3 grid((n + 255) / 256, (kc + 63) / 64);
       col_exp_kernel<<<grid, 256, 0, stream>>>(b, ldb, kc, n, eB);
     }
-    {
+    if (version == 3) {
+      const long long threads = (long long)m_pad * (kp / 16);
+      phpc::oz3::split_a_tiled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, SA, slices);
+      dim3 grid((unsigned)((n_pad + 127) / 128), kp / 32);
+      phpc::oz3::split_b_tiled_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, SB, slices);
+    } else {
       const long long threads = (long long)m * (kp / 16);
       split_a_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, SA, slices);
       dim3 grid((n + 127) / 128, kp / 32);
@@ -311,7 +318,23 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     CUtensorMap tmA, tmB;
     int grid = ctx->sm_count;
     if ((long long)grid > tiles) grid = (int)tiles;
-    if (version == 1) {
+    if (version == 3) {
+      namespace v3 = phpc::oz3;
+      v3::Params3 p;
+      p.C = dC;
+      p.ldc = ldc;
+      p.M = m;
+      p.N = n;
+      p.ksteps = kp / 32;
+      p.S = slices;
+      p.eA = eA;
+      p.eB = eB;
+      p.tiles_m = tiles_m;
+      p.tiles_n = tiles_n;
+      p.TA = SA;
+      p.TB = SB;
+      v3::ozaki_gemm_kernel_v3<<<grid, phpc::oz2::THREADS, phpc::oz2::SMEM_BYTES, stream>>>(p);
+    } else if (version == 1) {
       encode_map_bytes(&tmA, SA, kp, (long long)slices * m, BKB, BM);
       encode_map_bytes(&tmB, SB, kp, (long long)slices * n, BKB, BN);
       Params p;
