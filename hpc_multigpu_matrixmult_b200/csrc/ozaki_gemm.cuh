@@ -538,6 +538,8 @@ struct Params3 {
   int tiles_m, tiles_n;
   const int8_t *TA; /* [tiles_m][ksteps][S][4096] */
   const int8_t *TB; /* [tiles_n][ksteps][S][4096] */
+  int prefetch;     /* k steps of L2 prefetch ahead of the shared-memory ring (0 = off) */
+  int flags;        /* diagnostics: 1 = epilogue skips the C read-modify-write, 2 = no operand loads (MMA rate only) */
 };
 
 /* byte offset of element (row r < 128, k byte kb < 32) inside a canonical 4 KiB tile */
@@ -596,7 +598,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
 
   if (warp == 0) {
     /* ===== producer: two contiguous bulk copies per k step ===== */
-    if (lane == 0) {
+    if (lane == 0 && !(p.flags & 2)) {
       int stage = 0;
       uint32_t phase = 0;
       const size_t step_bytes = (size_t)S * TILE_BYTES;
@@ -615,6 +617,10 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
             bulk_load(sa, ta + (size_t)ks * step_bytes, bytes, full);
             bulk_load(sa + MAX_S * SLOT_BYTES, tb + (size_t)ks * step_bytes, bytes, full);
+            if (p.prefetch > 0 && ks + p.prefetch < p.ksteps) { /* pull the digits of a later k step into L2 */
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ta + (size_t)(ks + p.prefetch) * step_bytes), "r"(bytes) : "memory");
+              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tb + (size_t)(ks + p.prefetch) * step_bytes), "r"(bytes) : "memory");
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -637,7 +643,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
           mbar_wait(tempty, (unit & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           for (int ks = 0; ks < p.ksteps; ++ks) {
-            mbar_wait(full0 + 8 * stage, phase);
+            if (!(p.flags & 2)) mbar_wait(full0 + 8 * stage, phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
             const uint64_t da0 = smem_desc_kmajor_noswz(sa), db0 = smem_desc_kmajor_noswz(sa + MAX_S * SLOT_BYTES);
@@ -650,7 +656,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
                             (ks > 0 || t > t_lo) ? 1u : 0u);
               }
             }
-            oz::umma_commit(empty0 + 8 * stage);
+            if (!(p.flags & 2)) oz::umma_commit(empty0 + 8 * stage);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -699,13 +705,19 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
           const int col = tn * BN + c0 + lane;
           const int eb = (col < p.N) ? __ldg(p.eB + col) : ZERO_EXP;
           double *cptr = p.C + (long long)row0 * p.ldc + col;
-#pragma unroll 8
+          const bool col_ok = eb != ZERO_EXP && !(p.flags & 1);
+          /* all 32 row loads of this lane's column are issued before any is used: one memory
+           * round trip per 32x32 block instead of four */
+          double cold[32];
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) cold[rr] = (col_ok && rr < rows_here) ? cptr[(long long)rr * p.ldc] : 0.0;
+#pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
             double x;
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(tr + (uint32_t)(rr * 33 + lane) * 8) : "memory");
             const int er = __shfl_sync(0xffffffffu, ea, rr);
-            if (rr < rows_here && eb != ZERO_EXP && er != ZERO_EXP && x != 0.0)
-              cptr[(long long)rr * p.ldc] += x * oz::pow2d(er + eb - DIGIT_BITS * g_hi);
+            if (col_ok && rr < rows_here && er != ZERO_EXP && x != 0.0)
+              cptr[(long long)rr * p.ldc] = cold[rr] + x * oz::pow2d(er + eb - DIGIT_BITS * g_hi);
           }
           __syncwarp();
         }

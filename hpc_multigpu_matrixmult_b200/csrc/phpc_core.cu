@@ -333,6 +333,9 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
       p.tiles_n = tiles_n;
       p.TA = SA;
       p.TB = SB;
+      const char *pf = getenv("PHPC_OZ_PF"), *fl = getenv("PHPC_OZ_FLAGS");
+      p.prefetch = (pf && *pf) ? atoi(pf) : 6;
+      p.flags = (fl && *fl) ? atoi(fl) : 0;
       v3::ozaki_gemm_kernel_v3<<<grid, phpc::oz2::THREADS, phpc::oz2::SMEM_BYTES, stream>>>(p);
     } else if (version == 1) {
       encode_map_bytes(&tmA, SA, kp, (long long)slices * m, BKB, BM);
@@ -464,9 +467,19 @@ extern "C" void phpc_fill_host(double *h, long long ld, long long rows, long lon
 typedef void (*launch_fn)(DeviceCtx *, const double *, long long, const double *, long long, double *, long long, int, int, int, int,
                           cudaStream_t);
 
+/* PHPC_GEMM=ozaki routes the reference-named entry points through the tcgen05 (Ozaki) kernel
+ * instead of the native-FP64 DMMA kernel; both are sm_100a code, there is no other path. */
+bool phpc_use_ozaki(void) {
+  const char *g = getenv("PHPC_GEMM");
+  return g && !strcmp(g, "ozaki");
+}
+
 static void launch_dmma_adapter(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC,
                                 long long ldc, int m, int k, int n, int ctas, cudaStream_t s) {
-  phpc_launch_dmma(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctas, s);
+  if (phpc_use_ozaki())
+    phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, 0, s);
+  else
+    phpc_launch_dmma(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctas, s);
 }
 static void launch_cublas_adapter(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC,
                                   long long ldc, int m, int k, int n, int, cudaStream_t s) {

@@ -65,6 +65,7 @@ int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const doub
  * <= 0 picks PHPC_OZAKI_SLICES or 8); returns the number of kernels launched */
 int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                       int k, int n, int slices, cudaStream_t stream);
+bool phpc_use_ozaki(void); /* env PHPC_GEMM=ozaki */
 void phpc_launch_cublas(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                         int k, int n, cudaStream_t stream);
 

@@ -216,7 +216,7 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   s->m = n / s->r;
   s->n = n / s->c;
   s->pk = n / s->lcm;
-  if (kc <= 0) kc = env_int("PHPC_KC", s->size == 1 ? s->pk : 2048);
+  if (kc <= 0) kc = env_int("PHPC_KC", s->size == 1 ? s->pk : 4096);
   if (kc > s->pk) kc = s->pk;
   s->kc = kc;
   s->ldn = phpc_pad_ld(s->n);
@@ -788,7 +788,8 @@ extern "C" void phpc_gemm_summa_cuda(MPI_Comm grid_comm, const double *A, const 
   (void)gpu_count; /* one rank drives one GPU; see INTEGRATION.md */
   (void)block_width;
   const long long ctas = (long long)grid_width * grid_height;
-  summa_host(grid_comm, A, B, C, n, PHPC_BACKEND_DMMA, ctas > (1 << 20) ? (1 << 20) : (int)ctas, compute_time);
+  summa_host(grid_comm, A, B, C, n, phpc_use_ozaki() ? PHPC_BACKEND_OZAKI : PHPC_BACKEND_DMMA, ctas > (1 << 20) ? (1 << 20) : (int)ctas,
+             compute_time);
 }
 
 extern "C" void phpc_gemm_summa_cublas(MPI_Comm grid_comm, const double *A, const double *B, double *C, int n, int gpu_count,

@@ -74,7 +74,7 @@ typedef struct phpc_summa phpc_summa; /* opaque: blocks in HBM + NCCL row/col co
 /* Collective over grid_comm.  Binds the rank to a GPU (PHPC_DEVICE, else
  * LOCAL_RANK, else rank % device_count), builds/caches the NCCL communicators and
  * allocates the rank's A, B, C blocks and the receive ring in HBM.  kc <= 0 picks
- * the default (whole panel on a 1x1 grid, 2048 otherwise; env PHPC_KC overrides).
+ * the default (whole panel on a 1x1 grid, 4096 otherwise; env PHPC_KC overrides).
  * Panel transport (env PHPC_PANEL): "nccl" = ncclBroadcast on the row / column
  * communicators; "pull" (default) = each rank copies the chunks it does not own
  * straight out of the owner's HBM with the copy engines over NVLink (CUDA IPC peer

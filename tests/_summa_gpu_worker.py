@@ -36,9 +36,15 @@ def main():
     st = s.run()
     Cd = np.zeros((N, N))
     s.download_c(Cd, gather=True)
+    # the same loop with the tcgen05 (Ozaki) local GEMM
+    s.zero_c()
+    M.MPI_Barrier(capi.MPI_COMM_WORLD)
+    s.run(capi.BACKEND_OZAKI)
+    Co = np.zeros((N, N))
+    s.download_c(Co, gather=True)
     s.destroy()
     if rank == 0:
-        np.save(out, np.stack([C, Cb, Cd]))
+        np.save(out, np.stack([C, Cb, Cd, Co]))
         print(f"steps={st.steps} launches={st.launches} bcasts={st.broadcasts} rx={st.bytes_received} "
               f"total_ms={st.total_ms:.3f} gemm_ms={st.gemm_ms:.3f} exposed_ms={st.exposed_ms:.3f}")
     L.phpc_summa_release_cache()

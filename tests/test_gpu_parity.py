@@ -238,3 +238,88 @@ def test_main_out_cli_single_rank(gpu, tmp_path):
     res = subprocess.run([os.path.join(root, "bin", "main.out"), "64", "32", "1", "1", "nodir"], capture_output=True, text=True,
                          timeout=120, cwd=tmp_path / "csv")
     assert res.returncode != 0 and "Could not create CSV file" in res.stderr  # csv/ must pre-exist (reference :77-80)
+
+
+# ----------------------------------------------------------------------------------------------
+# FP64 on the tcgen05 tensor cores (Ozaki scheme, int8 digit products, int32 accumulators in TMEM)
+# ----------------------------------------------------------------------------------------------
+def _device_gemm_from_numpy(capi, lib, a, b, c0, backend, slices=0):
+    m, k = a.shape
+    n = b.shape[1]
+    lda, ldb = (k + 15) // 16 * 16, (n + 15) // 16 * 16
+    dA, dB, dC = lib.phpc_device_malloc(max(m * lda, 2) * 8), lib.phpc_device_malloc(max(k * ldb, 2) * 8), lib.phpc_device_malloc(max(m * ldb, 2) * 8)
+    lib.phpc_copy2d_to_device(dA, lda, capi._dp(a), k, m, k)
+    lib.phpc_copy2d_to_device(dB, ldb, capi._dp(b), n, k, n)
+    lib.phpc_copy2d_to_device(dC, ldb, capi._dp(c0), n, m, n)
+    if backend == "ozaki":
+        launched = lib.phpc_gemm_device_ozaki(dA, lda, dB, ldb, dC, ldb, m, k, n, slices, None)
+    else:
+        launched = lib.phpc_gemm_device(dA, lda, dB, ldb, dC, ldb, m, k, n, 0, None)
+    lib.phpc_device_synchronize()
+    out = capi.device_window(dC, ldb, 0, 0, m, n)
+    for p in (dA, dB, dC):
+        lib.phpc_device_free(p)
+    return out, launched
+
+
+@pytest.mark.parametrize("m,k,n", [(1, 1, 1), (128, 128, 128), (129, 33, 257), (100, 77, 50), (300, 215, 170), (512, 1024, 384), (257, 4100, 130)])
+def test_ozaki_gemm_seeded_vs_oracle(gpu, capi, oracle, m, k, n):
+    a = oracle.fill(m, k, kind=1, seed=101)
+    b = oracle.fill(k, n, kind=1, seed=202)
+    c0 = oracle.fill(m, n, kind=1, seed=303)
+    c, launched = _device_gemm_from_numpy(capi, gpu, a, b, c0, "ozaki")
+    assert launched >= 6  # exponent, split and MMA kernels of at least one K chunk
+    _check(oracle, c, oracle.gemm_block(a, b, c0), a, b)
+
+
+@pytest.mark.parametrize("n", [32, 200, 512, 1024])
+def test_ozaki_gemm_index_fill_bit_exact(gpu, capi, oracle, n):
+    """Digits carry the integers exactly and every int32 / FP64 partial sum is exact: 0 ulp."""
+    a = oracle.fill(n, n, kind=0)
+    c, _ = _device_gemm_from_numpy(capi, gpu, a, a.copy(), np.zeros((n, n)), "ozaki")
+    assert np.array_equal(c, oracle.index_fill_exact(n))
+
+
+def test_ozaki_gemm_row_and_column_scaling(gpu, capi, oracle):
+    """Per-row / per-column power-of-two scaling: rows and columns of wildly different magnitude
+    (2^-300 .. 2^+300), zero rows and zero columns keep full relative accuracy per C element."""
+    m, k, n = 96, 300, 80
+    a = oracle.fill(m, k, kind=1, seed=7)
+    b = oracle.fill(k, n, kind=1, seed=8)
+    a *= np.ldexp(1.0, np.linspace(-300, 300, m).astype(int))[:, None]
+    b *= np.ldexp(1.0, np.linspace(200, -200, n).astype(int))[None, :]
+    a[5, :] = 0.0
+    b[:, 9] = 0.0
+    c, _ = _device_gemm_from_numpy(capi, gpu, a, b, np.zeros((m, n)), "ozaki")
+    want = oracle.gemm_block(a, b)
+    scale = np.abs(a) @ np.abs(b) + 1e-300
+    assert np.all(np.abs(c - want) <= 4.0 * np.sqrt(k) * U * scale)
+    assert np.all(c[5, :] == 0.0) and np.all(c[:, 9] == 0.0)
+
+
+@pytest.mark.parametrize("slices,tol", [(4, 1e-6), (6, 1e-10), (7, 1e-12), (8, 1e-14)])
+def test_ozaki_digit_count_sets_the_accuracy(gpu, capi, oracle, slices, tol):
+    a = oracle.fill(256, 512, kind=1, seed=1)
+    b = oracle.fill(512, 256, kind=1, seed=2)
+    c, _ = _device_gemm_from_numpy(capi, gpu, a, b, np.zeros((256, 256)), "ozaki", slices)
+    assert oracle.rel_frobenius(c, oracle.gemm_block(a, b)) <= tol
+
+
+def test_summa_ozaki_backend_single_rank(gpu, capi, oracle):
+    n = 384
+    comm = capi.cart_create((1, 1))
+    A = oracle.fill(n, n, kind=1, seed=oracle.SEED_A)
+    B = oracle.fill(n, n, kind=1, seed=oracle.SEED_B)
+    want = oracle.gemm_block(A, B)
+    for kc in (0, 100):
+        s = capi.Summa(comm, n, kc)
+        s.fill(capi.FILL_SEEDED)
+        st = s.run(capi.BACKEND_OZAKI)
+        assert st.launches >= 6 * st.steps
+        assert oracle.rel_frobenius(s.read_c_block(), want) <= 1e-14
+        s.destroy()
+    s = capi.Summa(comm, 1024, 0)
+    s.fill(capi.FILL_INDEX)
+    s.run(capi.BACKEND_OZAKI)
+    assert np.array_equal(s.read_c_block(), oracle.index_fill_exact(1024))
+    s.destroy()

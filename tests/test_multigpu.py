@@ -40,7 +40,7 @@ def test_summa_matches_reference_summa_seeded(gpu, oracle, tmp_path, grid, ngpu)
     A = oracle.fill(N, N, kind=1, seed=oracle.SEED_A)
     B = oracle.fill(N, N, kind=1, seed=oracle.SEED_B)
     want = oracle.summa(A, B, *grid)
-    for name, C in zip(("host-entry dmma", "host-entry cublas", "device-resident"), Cs):
+    for name, C in zip(("host-entry dmma", "host-entry cublas", "device-resident dmma", "device-resident ozaki"), Cs):
         assert oracle.rel_frobenius(C, want) <= 1e-14, name
     assert "bcasts=" in log
 
