@@ -111,3 +111,22 @@ def test_schedule_drives_a_cpu_emulation_to_the_oracle_result(capi, oracle):
                 blk = oracle.gemm_block(a, b, blk)
             C[pi * m:(pi + 1) * m, pj * n:(pj + 1) * n] = blk
     assert oracle.rel_frobenius(C, oracle.summa(A, B, r, c)) < 1e-15
+
+
+def test_csv_runner_reads_the_reference_config_format(built, tmp_path):
+    """scripts/run_tests_csv.py consumes run-configuration CSVs in the reference's format (tests/*.csv)."""
+    import subprocess
+    import sys
+
+    cfg = tmp_path / "cfg.csv"
+    cfg.write_text("matrix_size,n_proc,n_gpu,tile_width,grid_width,grid_height\n128,1,1,32,1,1\n128,4,1,32,1,1\n512,8,2,16,2,2\n")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "run_tests_csv.py"), str(cfg), "--name", "t", "--dry-run"],
+                         capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].endswith("bin/main.out 128 32 1 1 t")
+    assert "mpirun --oversubscribe -n 4" in lines[1] and lines[1].endswith("main.out 128 32 1 1 t")
+    assert lines[2].startswith("PHPC_PGRID=2x4 ") and lines[2].endswith("main.out 512 16 2 2 t")
+    b200 = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "run_tests_csv.py"),
+                           os.path.join(ROOT, "tests", "configs", "b200_configs.csv"), "--dry-run"], capture_output=True, text=True, timeout=60)
+    assert b200.returncode == 0 and len(b200.stdout.strip().splitlines()) == 10

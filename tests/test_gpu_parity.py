@@ -323,3 +323,43 @@ def test_summa_ozaki_backend_single_rank(gpu, capi, oracle):
     s.run(capi.BACKEND_OZAKI)
     assert np.array_equal(s.read_c_block(), oracle.index_fill_exact(1024))
     s.destroy()
+
+
+@pytest.mark.parametrize("m,k,n", [(15000, 7500, 7500), (7500, 3750, 15000)])
+def test_config5_edge_tile_shapes_vs_cublas_and_exact_dots(gpu, capi, oracle, m, k, n):
+    """BASELINE config 5 (N=30000): the per-step local GEMM shapes of the 2x4 / 1x2 grids — none of
+    m, k, n is a multiple of the 128 / 16 tile.  DMMA and Ozaki kernels vs cuBLAS on the same device
+    inputs, plus sampled elements against correctly rounded dot products."""
+    lib = gpu
+    lda, ldb = (k + 15) // 16 * 16, (n + 15) // 16 * 16
+    dA, dB = lib.phpc_device_malloc(m * lda * 8), lib.phpc_device_malloc(k * ldb * 8)
+    lib.phpc_fill_device(dA, lda, m, k, 0, 0, k, capi.FILL_SEEDED, 31, None)
+    lib.phpc_fill_device(dB, ldb, k, n, 0, 0, n, capi.FILL_SEEDED, 32, None)
+    outs = {}
+    for name in ("cublas", "dmma", "ozaki"):
+        dC = lib.phpc_device_malloc(m * ldb * 8)
+        lib.phpc_device_memset(dC, 0, m * ldb * 8)
+        if name == "cublas":
+            lib.phpc_gemm_device_cublas(dA, lda, dB, ldb, dC, ldb, m, k, n, None)
+        elif name == "dmma":
+            lib.phpc_gemm_device(dA, lda, dB, ldb, dC, ldb, m, k, n, 0, None)
+        else:
+            lib.phpc_gemm_device_ozaki(dA, lda, dB, ldb, dC, ldb, m, k, n, 0, None)
+        lib.phpc_device_synchronize()
+        # last rows / last columns: the edge tiles
+        outs[name] = (capi.device_window(dC, ldb, m - 200, n - 300, 200, 300), capi.device_window(dC, ldb, 0, 0, 64, n))
+        lib.phpc_device_free(dC)
+    for name in ("dmma", "ozaki"):
+        for w, wref in zip(outs[name], outs["cublas"]):
+            assert oracle.rel_frobenius(w, wref) <= 1e-14, name
+    a_rows = capi.device_window(dA, lda, m - 3, 0, 3, k)
+    b_all = capi.device_window(dB, ldb, 0, n - 300, k, 300)
+    for name in ("dmma", "ozaki"):
+        edge = outs[name][0]
+        for i in range(3):
+            for j in (0, 150, 299):
+                exact = oracle.dot_exact(a_rows[i], np.ascontiguousarray(b_all[:, j]))
+                bound = 4.0 * np.sqrt(k) * U * float(np.abs(a_rows[i]) @ np.abs(b_all[:, j]))
+                assert abs(edge[200 - 3 + i, j] - exact) <= bound, name
+    lib.phpc_device_free(dA)
+    lib.phpc_device_free(dB)

@@ -97,3 +97,17 @@ def test_main_out_cli_multi_rank(gpu, tmp_path):
         assert res.returncode == 0, res.stdout + res.stderr
         line = open(tmp_path / "csv" / "testA_N1024_T2_G1_TW32_GW1_GH1.csv").read().strip().split(",")
         assert line[:6] == ["1024", "2", "1", "1", "1024", "1024"] and len(line) == 9
+
+
+@pytest.mark.parametrize("tile_width", [16, 32, 64, 128, 256])
+def test_config5_n30000_tile_width_sweep_1x2(gpu, tmp_path, tile_width):
+    """BASELINE config 5: non-divisible N=30000 on the rectangular 1x2 grid, every tile_width of the
+    sweep; main.out verifies sampled elements of every rank's block against the closed form."""
+    _need(gpu, 2)
+    (tmp_path / "csv").mkdir()
+    env = dict(os.environ, PHPC_VERIFY="1", PHPC_MODE="device", PHPC_PGRID="1x2")
+    res = subprocess.run([os.path.join(ROOT, "bin", "mpirun"), "-n", "2", os.path.join(ROOT, "bin", "main.out"), "30000", str(tile_width), "1", "1",
+                          "cfg5"], capture_output=True, text=True, timeout=300, cwd=tmp_path, env=env)
+    assert res.returncode == 0, res.stdout + res.stderr
+    rec = open(tmp_path / "csv" / f"cfg5_N30000_T2_G1_TW{tile_width}_GW1_GH1.csv").read().strip().split(",")
+    assert rec[0] == "30000" and rec[1] == "2" and float(rec[6]) > 0
