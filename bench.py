@@ -41,6 +41,7 @@ METRIC = "summa_gemm_tflops"
 UNIT = "TFLOP/s"
 GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
 CPU_SAMPLE_N = 1024
+DMMA_N32768_DRAM_BYTES = 1513196364800 + 8660417536  # one ncu capture of the N=32768 launch (profiles/ncu_dmma_n32768_dram_r01.csv)
 
 
 # ----------------------------------------------------------------------------
@@ -381,7 +382,10 @@ def product_arm(args):
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": kernel_tflops, "peak": peak, "unit": UNIT, "frac": kernel_tflops / peak,
-                         "traffic": None, "kernel": "phpc::dmma_gemm_kernel (FP64 DMMA.8x8x4, TMA + mbarrier pipeline)",
+                         "traffic": DMMA_N32768_DRAM_BYTES if (world == 1 and N == 32768 and steps_per_summa == 1) else None,
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this launch shape, profiles/ncu_dmma_n32768_dram_r01.csv "
+                                           "(compute bound: 12 % of HBM bandwidth; L2 hit rate of the A/B panel re-reads ~66 %)",
+                         "kernel": "phpc::dmma_gemm_kernel (FP64 DMMA.8x8x4, TMA + mbarrier pipeline)",
                          "flops_per_launch": 2.0 * m_blk * n_blk * k_per_launch, "kernel_ms": kernel_ms, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "tcgen05_ozaki": ozaki,
