@@ -90,6 +90,21 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+/* one lane of a fully converged warp (the others skip): keeps the surrounding code warp-uniform so
+ * descriptors and addresses stay in uniform registers instead of being moved there per MMA */
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, int (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -561,6 +576,7 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                : "memory");
 }
 
+template <int S_T>
 __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3 p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -573,7 +589,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
-  const int S = p.S;
+  const int S = S_T > 0 ? S_T : p.S; /* compile-time digit count: the MMA issue loops unroll into straight-line uniform code */
   const int npass = (S + GROUPS_PER_PASS - 1) / GROUPS_PER_PASS;
 
   if (threadIdx.x == 0) {
@@ -630,8 +646,10 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
       }
     }
   } else if (warp == 1) {
-    /* ===== MMA issuer ===== */
-    if (lane == 0) {
+    /* ===== MMA issuer: the whole warp walks the loops (uniform control flow and addresses), one
+     * elected lane issues tcgen05.mma / tcgen05.commit.  With the loops inside `if (lane == 0)` every
+     * MMA cost ~140-180 cycles of register->uniform-register traffic (tools/umma_rate.cu). ===== */
+    {
       const uint32_t idesc = oz::idesc_i8(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -647,22 +665,42 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
             const uint64_t da0 = smem_desc_kmajor_noswz(sa), db0 = smem_desc_kmajor_noswz(sa + MAX_S * SLOT_BYTES);
-            for (int g = g_hi; g >= g_lo; --g) {
-              const uint32_t tacc = tmem_base + (uint32_t)(g - g_lo) * BN;
-              const int t_lo = max(1, g - S), t_hi = min(S, g - 1);
-              for (int t = t_lo; t <= t_hi; ++t) {
-                const int u = g - t;
-                oz::umma_i8(tacc, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)), db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc,
-                            (ks > 0 || t > t_lo) ? 1u : 0u);
+            const uint32_t first = ks > 0 ? 1u : 0u;
+            if (oz::elect_one()) {
+              if (S_T > 0) {
+                /* fully unrolled: every (group, digit pair) of the pass with immediate descriptor offsets */
+#pragma unroll
+                for (int gi = 0; gi < GROUPS_PER_PASS; ++gi) {
+#pragma unroll
+                  for (int t = 1; t <= MAX_S; ++t) {
+                    const int g = g_hi - gi;
+                    const int u = g - t;
+                    if (g >= g_lo && t <= S && u >= 1 && u <= S)
+                      oz::umma_i8(tmem_base + (uint32_t)(g - g_lo) * BN, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)),
+                                  db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc, (t > max(1, g - S)) ? 1u : first);
+                  }
+                }
+              } else {
+                for (int g = g_hi; g >= g_lo; --g) {
+                  const uint32_t tacc = tmem_base + (uint32_t)(g - g_lo) * BN;
+                  const int t_lo = max(1, g - S), t_hi = min(S, g - 1);
+                  for (int t = t_lo; t <= t_hi; ++t) {
+                    const int u = g - t;
+                    oz::umma_i8(tacc, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)), db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc,
+                                (t > t_lo) ? 1u : first);
+                  }
+                }
               }
+              if (!(p.flags & 2)) oz::umma_commit(empty0 + 8 * stage);
             }
-            if (!(p.flags & 2)) oz::umma_commit(empty0 + 8 * stage);
+            __syncwarp();
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
           }
-          oz::umma_commit(tfull);
+          if (oz::elect_one()) oz::umma_commit(tfull);
+          __syncwarp();
         }
       }
     }

@@ -87,7 +87,8 @@ DeviceCtx *phpc_ctx(int device) {
   CUDA_CHECK(cudaFuncSetAttribute(phpc::dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::GEMM_SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz2::ozaki_gemm_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz2::SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz3::ozaki_gemm_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz2::SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz3::ozaki_gemm_kernel_v3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz2::SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz3::ozaki_gemm_kernel_v3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz2::SMEM_BYTES));
   load_driver_entry_points();
   ctx->ready = true;
   return ctx;
@@ -336,7 +337,10 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
       const char *pf = getenv("PHPC_OZ_PF"), *fl = getenv("PHPC_OZ_FLAGS");
       p.prefetch = (pf && *pf) ? atoi(pf) : 6;
       p.flags = (fl && *fl) ? atoi(fl) : 0;
-      v3::ozaki_gemm_kernel_v3<<<grid, phpc::oz2::THREADS, phpc::oz2::SMEM_BYTES, stream>>>(p);
+      if (slices == 8)
+        v3::ozaki_gemm_kernel_v3<8><<<grid, phpc::oz2::THREADS, phpc::oz2::SMEM_BYTES, stream>>>(p);
+      else
+        v3::ozaki_gemm_kernel_v3<0><<<grid, phpc::oz2::THREADS, phpc::oz2::SMEM_BYTES, stream>>>(p);
     } else if (version == 1) {
       encode_map_bytes(&tmA, SA, kp, (long long)slices * m, BKB, BM);
       encode_map_bytes(&tmB, SB, kp, (long long)slices * n, BKB, BN);
