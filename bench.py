@@ -162,6 +162,16 @@ def fp64_peak():
         return nominal, f"fallback: nominal FP64 148 SM x 64 FMA/clk x 1965 MHz = {nominal:.1f} TFLOP/s (profiles/fp64_peak_r01.json missing)"
 
 
+def int8_peak():
+    """int8 tensor roofline: tcgen05.mma kind::i8 issue-rate microbenchmark on this pool (tools/umma_rate.cu)."""
+    path = os.path.join(ROOT, "profiles", "umma_rate_r01.jsonl")
+    try:
+        best = max(json.loads(l)["chip_tops_at_event_time"] for l in open(path) if '"kind": "i8"' in l)
+        return best, f"measured int8 tensor peak {best:.0f} TOP/s (tcgen05.mma kind::i8 128x256x32 issue rate, all SMs, burst clocks; profiles/umma_rate_r01.jsonl)"
+    except (OSError, ValueError, KeyError):
+        return 2.0 * 1590.0, "fallback: 2 x bf16 fallback peak (profiles/umma_rate_r01.jsonl missing)"
+
+
 def host_matrices(capi, N, dims, coords, pin=True):
     """FULL N x N host A, B, C as the reference API wants them; only the windows this rank
     owns are filled and page-locked (the rest of the address range is never touched)."""
@@ -263,75 +273,75 @@ def product_arm(args):
     flops = 2.0 * N ** 3
 
     # ---------------- device-resident SUMMA: `value` ----------------
+    # primary = the kernel the reference-named entry points run (tcgen05 Ozaki unless PHPC_GEMM=dmma);
+    # the other kernel is measured right after it on the same blocks and reported beside it.
+    primary = capi.BACKEND_DMMA if os.environ.get("PHPC_GEMM") == "dmma" else capi.BACKEND_OZAKI
+    secondary = capi.BACKEND_OZAKI if primary == capi.BACKEND_DMMA else capi.BACKEND_DMMA
+    names = {capi.BACKEND_DMMA: "native_fp64_dmma", capi.BACKEND_OZAKI: "tcgen05_ozaki"}
     s = capi.Summa(comm, N, args.kc)
     s.fill(capi.FILL_SEEDED)
     stream = torch.cuda.current_stream()
     sptr = ctypes.c_void_p(stream.cuda_stream)
-    for _ in range(args.warmup):
-        s.run(capi.BACKEND_DMMA, 0, sptr, stats=False)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_begin = time.perf_counter()
-    e0.record(stream)
-    st = None
-    for i in range(args.steps):
-        last = i == args.steps - 1
-        st = s.run(capi.BACKEND_DMMA, 0, sptr, stats=last)  # per-launch events are read on the last step
-    e1.record(stream)
-    torch.cuda.synchronize()
-    barrier()
-    t_end = time.perf_counter()
-    ms_per_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
-    value = flops / (ms_per_step * 1e-3) / 1e12
+    slices = int(os.environ.get("PHPC_OZAKI_SLICES", "8"))
+    pairs = slices * (slices + 1) // 2
+    fp64_pk, fp64_src = fp64_peak()
+    int8_pk, int8_src = int8_peak()
 
+    def measure(backend, warmup, steps, sample_clocks):
+        for _ in range(warmup):
+            s.run(backend, 0, sptr, stats=False)
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and sample_clocks:
+            sampler.start()
+            time.sleep(0.3)
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin = time.perf_counter()
+        e0.record(stream)
+        st = None
+        for i in range(steps):
+            st = s.run(backend, 0, sptr, stats=(i == steps - 1))  # per-launch events are read on the last step
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        t_end = time.perf_counter()
+        ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+        clocks = sampler.stop(t_begin, t_end) if (rank == 0 and sample_clocks) else None
+        m_blk, n_blk = s.block
+        k_per_gemm = N / st.steps
+        gemm_ms = st.gemm_ms / st.steps  # mean duration of one local GEMM (device events around every launch)
+        gemm_tflops = 2.0 * m_blk * n_blk * k_per_gemm / (gemm_ms * 1e-3) / 1e12
+        if backend == capi.BACKEND_OZAKI:
+            roof = {"bound": "tensor", "achieved": gemm_tflops * pairs, "peak": int8_pk, "unit": "TOP/s", "frac": gemm_tflops * pairs / int8_pk,
+                    "traffic": None, "kernel": "phpc::oz3::ozaki_gemm_kernel_v3<8> (tcgen05.mma kind::i8, int32 accumulators in TMEM, cp.async.bulk ring)",
+                    "ops_per_launch": 2.0 * m_blk * n_blk * k_per_gemm * pairs, "kernel_ms": gemm_ms, "fp64_equivalent_tflops": gemm_tflops,
+                    "fp64_equivalent_vs_fp64_peak": gemm_tflops / fp64_pk, "peak_source": int8_src,
+                    "note": f"{pairs} int8 MMAs per FP64 MMA ({slices} digits); kernel_ms spans the whole local GEMM (exponent + split kernels "
+                            "included, < 3 % at this size)"}
+        else:
+            roof = {"bound": "tensor", "achieved": gemm_tflops, "peak": fp64_pk, "unit": UNIT, "frac": gemm_tflops / fp64_pk,
+                    "traffic": DMMA_N32768_DRAM_BYTES if (world == 1 and N == 32768 and st.steps == 1) else None,
+                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this launch shape, profiles/ncu_dmma_n32768_dram_r01.csv "
+                                      "(compute bound: 12 % of HBM bandwidth; L2 hit rate of the A/B panel re-reads ~66 %)",
+                    "kernel": "phpc::dmma_gemm_kernel (FP64 DMMA.8x8x4, TMA + mbarrier pipeline)",
+                    "flops_per_launch": 2.0 * m_blk * n_blk * k_per_gemm, "kernel_ms": gemm_ms, "peak_source": fp64_src}
+        return {"tflops": flops / (ms * 1e-3) / 1e12, "ms": ms, "clocks": clocks, "stats": st, "roofline": roof,
+                "exposed": max_over_ranks(st.exposed_ms / st.total_ms if st.total_ms > 0 else 0.0)}
+
+    prim = measure(primary, args.warmup, args.steps, True)
+    value, ms_per_step, clocks, st = prim["tflops"], prim["ms"], prim["clocks"], prim["stats"]
+    exposed_frac = prim["exposed"]
     launches_per_step = st.launches
-    kernel_ms = st.gemm_ms / max(st.launches, 1)
-    m_blk, n_blk = s.block
-    k_per_launch = N / st.steps
-    kernel_tflops = 2.0 * m_blk * n_blk * k_per_launch / (kernel_ms * 1e-3) / 1e12
-    exposed_frac = max_over_ranks(st.exposed_ms / st.total_ms if st.total_ms > 0 else 0.0)
-    peak, peak_src = fp64_peak()
     bytes_rx = st.bytes_received
     steps_per_summa = st.steps
-    kc_used = int(k_per_launch)
-
-    # ---- the same SUMMA with the tcgen05 local GEMM (FP64 rebuilt from int8 MMAs, TMEM accumulators) ----
-    ozaki = None
-    if not args.no_ozaki:
-        s.run(capi.BACKEND_OZAKI, 0, sptr, stats=False)  # warm-up (allocates the digit scratch)
-        torch.cuda.synchronize()
-        barrier()
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        o0.record(stream)
-        osteps = max(1, min(2, args.steps))
-        ost = None
-        for i in range(osteps):
-            ost = s.run(capi.BACKEND_OZAKI, 0, sptr, stats=(i == osteps - 1))
-        o1.record(stream)
-        torch.cuda.synchronize()
-        barrier()
-        oms = max_over_ranks(o0.elapsed_time(o1) / osteps)
-        slices = int(os.environ.get("PHPC_OZAKI_SLICES", "8"))
-        pairs = slices * (slices + 1) // 2
-        otf = flops / (oms * 1e-3) / 1e12
-        per_gpu_int8_tops = otf * pairs / world
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-        int8_peak = 2.0 * peaks.get("bf16_tflops", 1590.0)
-        ozaki = {"value": otf, "unit": UNIT, "ms_per_step": oms, "steps": osteps, "slices": slices, "int8_mma_per_fp64_mma": pairs,
-                 "exposed_frac": max_over_ranks(ost.exposed_ms / ost.total_ms if ost.total_ms > 0 else 0.0),
-                 "kernels_per_step": ost.launches,
-                 "roofline": {"bound": "tensor", "achieved": per_gpu_int8_tops, "unit": "TOP/s (int8, per GPU)", "peak": int8_peak,
-                              "frac": per_gpu_int8_tops / int8_peak,
-                              "peak_source": "2 x measured bf16 burst of MEASURED_PEAKS.json (int8 dense is nominally 2x bf16; not measured directly)"},
-                 "note": "same device-resident SUMMA, local GEMM = phpc::oz3::ozaki_gemm_kernel_v3 (tcgen05.mma kind::i8, TMEM accumulators); "
-                         "includes the exponent/split kernels of every K chunk"}
+    kc_used = int(N / st.steps)
+    other = None
+    if not args.no_secondary:
+        sec = measure(secondary, 1, max(1, min(2, args.steps)), False)
+        other = {"value": sec["tflops"], "unit": UNIT, "ms_per_step": sec["ms"], "exposed_frac": sec["exposed"],
+                 "kernels_per_step": sec["stats"].launches, "roofline": sec["roofline"]}
     s.destroy()
 
     # ---------------- e2e through the reference-facing C-ABI on host matrices ----------------
@@ -374,21 +384,20 @@ def product_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"SUMMA C+=A*B, N={N}, FP64, splitmix64-seeded uniform(-1,1) A/B generated in HBM, owned blocks device-resident",
+            "config": {"workload": f"SUMMA C+=A*B, N={N}, FP64 in/out, splitmix64-seeded uniform(-1,1) A/B generated in HBM, owned blocks device-resident",
+                       "local_gemm": names[primary],
+                       "arithmetic": ("FP64 rebuilt exactly from 8 signed 7-bit digits per operand: s8 x s8 -> s32 on tcgen05, FP64 recombination "
+                                      "(rel. Frobenius difference to native FP64 1.5e-15)") if primary == capi.BACKEND_OZAKI else "native FP64 DMMA",
                        "N": N, "process_grid": f"{dims[0]}x{dims[1]}", "k_chunk": kc_used, "summa_steps": steps_per_summa,
                        "cache": "inputs_larger_than_l2 (operands are GiBs; L2 is 126 MB)", "exposed_broadcast_frac": exposed_frac,
                        "nvlink_bytes_received_rank0_per_step": bytes_rx},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "tensor", "achieved": kernel_tflops, "peak": peak, "unit": UNIT, "frac": kernel_tflops / peak,
-                         "traffic": DMMA_N32768_DRAM_BYTES if (world == 1 and N == 32768 and steps_per_summa == 1) else None,
-                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this launch shape, profiles/ncu_dmma_n32768_dram_r01.csv "
-                                           "(compute bound: 12 % of HBM bandwidth; L2 hit rate of the A/B panel re-reads ~66 %)",
-                         "kernel": "phpc::dmma_gemm_kernel (FP64 DMMA.8x8x4, TMA + mbarrier pipeline)",
-                         "flops_per_launch": 2.0 * m_blk * n_blk * k_per_launch, "kernel_ms": kernel_ms, "peak_source": peak_src},
+            "roofline": prim["roofline"],
             "cpu_baseline": cpu,
-            "tcgen05_ozaki": ozaki,
+            "local_gemm": names[primary],
+            names[secondary]: other,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -412,7 +421,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-ozaki", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the second local-GEMM kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -47,6 +47,7 @@ constexpr int TMEM_COLS = 512; /* two int32 accumulators of 256 columns */
 constexpr int DIGIT_BITS = 7;
 constexpr int MAX_SLICES = 8;
 constexpr int ZERO_EXP = -2147483647 - 1; /* exponent of an all-zero row / column */
+constexpr int NONFINITE_EXP = 2147483647; /* the row / column holds an Inf or NaN: its C elements become NaN */
 
 struct Params {
   double *C;
@@ -625,17 +626,24 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
         const int8_t *tb = p.TB + (size_t)tn * p.ksteps * step_bytes;
         for (int ps = 0; ps < npass; ++ps) {
           const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
-          const uint32_t bytes = (uint32_t)min(S, g_hi - 1) * TILE_BYTES; /* digits 1 .. d_hi */
-          for (int ks = 0; ks < p.ksteps; ++ks) {
+          const int d_hi = min(S, g_hi - 1);                      /* digits 1 .. d_hi take part in this pass */
+          const uint32_t bytes = (uint32_t)d_hi * TILE_BYTES;
+          const int sub = (2 * d_hi <= MAX_S) ? 2 : 1;            /* a pass that needs <= half the digit slots packs 2 k steps per stage */
+          for (int ks = 0; ks < p.ksteps; ks += sub) {
+            const int nsub = min(sub, p.ksteps - ks);
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             const uint32_t full = full0 + 8 * stage;
-            mbar_expect_tx(full, 2 * bytes);
+            mbar_expect_tx(full, 2 * bytes * nsub);
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            bulk_load(sa, ta + (size_t)ks * step_bytes, bytes, full);
-            bulk_load(sa + MAX_S * SLOT_BYTES, tb + (size_t)ks * step_bytes, bytes, full);
+            for (int h = 0; h < nsub; ++h) {
+              bulk_load(sa + h * d_hi * SLOT_BYTES, ta + (size_t)(ks + h) * step_bytes, bytes, full);
+              bulk_load(sa + (MAX_S + h * d_hi) * SLOT_BYTES, tb + (size_t)(ks + h) * step_bytes, bytes, full);
+            }
             if (p.prefetch > 0 && ks + p.prefetch < p.ksteps) { /* pull the digits of a later k step into L2 */
-              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ta + (size_t)(ks + p.prefetch) * step_bytes), "r"(bytes) : "memory");
-              asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tb + (size_t)(ks + p.prefetch) * step_bytes), "r"(bytes) : "memory");
+              for (int h = 0; h < nsub; ++h) {
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ta + (size_t)(ks + h + p.prefetch) * step_bytes), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tb + (size_t)(ks + h + p.prefetch) * step_bytes), "r"(bytes) : "memory");
+              }
             }
             if (++stage == STAGES) {
               stage = 0;
@@ -660,34 +668,40 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
           const int g_lo = max(2, g_hi - GROUPS_PER_PASS + 1);
           mbar_wait(tempty, (unit & 1) ^ 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int ks = 0; ks < p.ksteps; ++ks) {
+          const int d_hi = min(S, g_hi - 1);
+          const int sub = (2 * d_hi <= MAX_S) ? 2 : 1;
+          for (int ks = 0; ks < p.ksteps; ks += sub) {
+            const int nsub = min(sub, p.ksteps - ks);
             if (!(p.flags & 2)) mbar_wait(full0 + 8 * stage, phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            const uint64_t da0 = smem_desc_kmajor_noswz(sa), db0 = smem_desc_kmajor_noswz(sa + MAX_S * SLOT_BYTES);
-            const uint32_t first = ks > 0 ? 1u : 0u;
             if (oz::elect_one()) {
-              if (S_T > 0) {
-                /* fully unrolled: every (group, digit pair) of the pass with immediate descriptor offsets */
+              for (int h = 0; h < nsub; ++h) {
+                const uint64_t da0 = smem_desc_kmajor_noswz(sa + h * d_hi * SLOT_BYTES);
+                const uint64_t db0 = smem_desc_kmajor_noswz(sa + (MAX_S + h * d_hi) * SLOT_BYTES);
+                const uint32_t first = (ks + h) > 0 ? 1u : 0u;
+                if (S_T > 0) {
+                  /* fully unrolled: every (group, digit pair) of the pass with immediate descriptor offsets */
 #pragma unroll
-                for (int gi = 0; gi < GROUPS_PER_PASS; ++gi) {
+                  for (int gi = 0; gi < GROUPS_PER_PASS; ++gi) {
 #pragma unroll
-                  for (int t = 1; t <= MAX_S; ++t) {
-                    const int g = g_hi - gi;
-                    const int u = g - t;
-                    if (g >= g_lo && t <= S && u >= 1 && u <= S)
-                      oz::umma_i8(tmem_base + (uint32_t)(g - g_lo) * BN, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)),
-                                  db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc, (t > max(1, g - S)) ? 1u : first);
+                    for (int t = 1; t <= MAX_S; ++t) {
+                      const int g = g_hi - gi;
+                      const int u = g - t;
+                      if (g >= g_lo && t <= S && u >= 1 && u <= S)
+                        oz::umma_i8(tmem_base + (uint32_t)(g - g_lo) * BN, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)),
+                                    db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc, (t > max(1, g - S)) ? 1u : first);
+                    }
                   }
-                }
-              } else {
-                for (int g = g_hi; g >= g_lo; --g) {
-                  const uint32_t tacc = tmem_base + (uint32_t)(g - g_lo) * BN;
-                  const int t_lo = max(1, g - S), t_hi = min(S, g - 1);
-                  for (int t = t_lo; t <= t_hi; ++t) {
-                    const int u = g - t;
-                    oz::umma_i8(tacc, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)), db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc,
-                                (t > t_lo) ? 1u : first);
+                } else {
+                  for (int g = g_hi; g >= g_lo; --g) {
+                    const uint32_t tacc = tmem_base + (uint32_t)(g - g_lo) * BN;
+                    const int t_lo = max(1, g - S), t_hi = min(S, g - 1);
+                    for (int t = t_lo; t <= t_hi; ++t) {
+                      const int u = g - t;
+                      oz::umma_i8(tacc, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)), db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc,
+                                  (t > t_lo) ? 1u : first);
+                    }
                   }
                 }
               }
@@ -754,8 +768,12 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
             double x;
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(tr + (uint32_t)(rr * 33 + lane) * 8) : "memory");
             const int er = __shfl_sync(0xffffffffu, ea, rr);
-            if (col_ok && rr < rows_here && er != ZERO_EXP && x != 0.0)
-              cptr[(long long)rr * p.ldc] = cold[rr] + x * oz::pow2d(er + eb - DIGIT_BITS * g_hi);
+            if (col_ok && rr < rows_here) {
+              if (er == oz::NONFINITE_EXP || eb == oz::NONFINITE_EXP)
+                cptr[(long long)rr * p.ldc] = __longlong_as_double(0x7ff8000000000000ll); /* Inf/NaN in the row or column */
+              else if (er != ZERO_EXP && x != 0.0)
+                cptr[(long long)rr * p.ldc] = cold[rr] + x * oz::pow2d(er + eb - DIGIT_BITS * g_hi);
+            }
           }
           __syncwarp();
         }

@@ -25,6 +25,7 @@ __device__ __forceinline__ int exp_above(double x) { /* smallest e with |x| < 2^
   const int lo = __double2loint(x);
   if ((hi | lo) == 0) return ZERO_EXP;
   const int biased = hi >> 20;
+  if (biased == 0x7ff) return NONFINITE_EXP;       /* Inf / NaN poisons the row / column */
   return biased == 0 ? -1022 : biased - 1023 + 1; /* denormals share the smallest normal exponent */
 }
 
@@ -147,7 +148,7 @@ __global__ void split_a_tiled_kernel(const double *__restrict__ A, long long lda
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int c = c0 + j;
-    r[j] = (row < m && c < k && e != oz::ZERO_EXP) ? scalbn(A[(long long)row * lda + c], -e) : 0.0;
+    r[j] = (row < m && c < k && e != oz::ZERO_EXP && e != oz::NONFINITE_EXP) ? scalbn(A[(long long)row * lda + c], -e) : 0.0;
   }
   const int ksteps = kp / 32;
   const size_t base = (((size_t)(row >> 7) * ksteps + (c0 >> 5)) * S) * 4096 + tile_offset(row & 127, c0 & 31);
@@ -180,7 +181,7 @@ __global__ void split_b_tiled_kernel(const double *__restrict__ B, long long ldb
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const int row = k0 + j;
-    r[j] = (col < n && row < k && e != oz::ZERO_EXP) ? scalbn(B[(long long)row * ldb + col], -e) : 0.0;
+    r[j] = (col < n && row < k && e != oz::ZERO_EXP && e != oz::NONFINITE_EXP) ? scalbn(B[(long long)row * ldb + col], -e) : 0.0;
   }
   const int ksteps = kp / 32;
   const size_t base = (((size_t)(col >> 7) * ksteps + ks) * S) * 4096 + tile_offset(col & 127, 0);

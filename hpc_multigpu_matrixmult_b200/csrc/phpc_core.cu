@@ -335,7 +335,7 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
       p.TA = SA;
       p.TB = SB;
       const char *pf = getenv("PHPC_OZ_PF"), *fl = getenv("PHPC_OZ_FLAGS");
-      p.prefetch = (pf && *pf) ? atoi(pf) : 6;
+      p.prefetch = (pf && *pf) ? atoi(pf) : 0; /* measured: no gain (profiles/ozaki_experiments_r01.md) */
       p.flags = (fl && *fl) ? atoi(fl) : 0;
       if (slices == 8)
         v3::ozaki_gemm_kernel_v3<8><<<grid, phpc::oz2::THREADS, phpc::oz2::SMEM_BYTES, stream>>>(p);
@@ -471,11 +471,12 @@ extern "C" void phpc_fill_host(double *h, long long ld, long long rows, long lon
 typedef void (*launch_fn)(DeviceCtx *, const double *, long long, const double *, long long, double *, long long, int, int, int, int,
                           cudaStream_t);
 
-/* PHPC_GEMM=ozaki routes the reference-named entry points through the tcgen05 (Ozaki) kernel
- * instead of the native-FP64 DMMA kernel; both are sm_100a code, there is no other path. */
+/* Which kernel the reference-named entry points (phpc_gemm_cuda, phpc_gemm_summa_cuda) run.
+ * Default: the tcgen05/TMEM kernel (FP64 rebuilt from int8 MMAs, 8 digits); PHPC_GEMM=dmma selects
+ * the native-FP64 DMMA kernel.  Both are sm_100a code; there is no other path. */
 bool phpc_use_ozaki(void) {
   const char *g = getenv("PHPC_GEMM");
-  return g && !strcmp(g, "ozaki");
+  return !(g && !strcmp(g, "dmma"));
 }
 
 static void launch_dmma_adapter(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC,

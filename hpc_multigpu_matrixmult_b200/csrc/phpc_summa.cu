@@ -776,7 +776,7 @@ static void summa_host(MPI_Comm grid_comm, const double *A, const double *B, dou
   }
   if (!s) {
     /* K chunks of 2048 columns even on one GPU: the uploads pipeline under the GEMMs */
-    s = g_host_plan = phpc_summa_create(grid_comm, n, env_int("PHPC_KC", 2048));
+    s = g_host_plan = phpc_summa_create(grid_comm, n, env_int("PHPC_KC", phpc_use_ozaki() ? 4096 : 2048));
   }
   phpc_summa_stats stats;
   phpc_summa_run_host(s, backend, ctas, A, B, C, 1, &stats);

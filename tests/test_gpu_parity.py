@@ -363,3 +363,42 @@ def test_config5_edge_tile_shapes_vs_cublas_and_exact_dots(gpu, capi, oracle, m,
                 assert abs(edge[200 - 3 + i, j] - exact) <= bound, name
     lib.phpc_device_free(dA)
     lib.phpc_device_free(dB)
+
+
+def test_entry_points_default_to_tcgen05_and_dmma_is_selectable(gpu, capi, oracle):
+    """phpc_gemm_cuda runs the tcgen05 (Ozaki) kernel unless PHPC_GEMM=dmma; both meet the same bar."""
+    import os
+
+    m, k, n = 200, 333, 150
+    a = oracle.fill(m, k, kind=1, seed=41)
+    b = oracle.fill(k, n, kind=1, seed=42)
+    want = oracle.gemm_block(a, b)
+    results = {}
+    for mode in ("ozaki", "dmma"):
+        os.environ["PHPC_GEMM"] = mode
+        c = np.zeros((m, n))
+        capi.phpc_gemm_cuda(a, b, c)
+        _check(oracle, c, want, a, b)
+        results[mode] = c
+    del os.environ["PHPC_GEMM"]
+    c = np.zeros((m, n))
+    capi.phpc_gemm_cuda(a, b, c)
+    assert np.array_equal(c, results["ozaki"])           # the default is the tcgen05 kernel
+    assert not np.array_equal(results["ozaki"], results["dmma"])  # different summation orders, same tolerance
+
+
+def test_ozaki_nonfinite_inputs_poison_their_row_and_column(gpu, capi, oracle):
+    m, k, n = 64, 96, 80
+    a = oracle.fill(m, k, kind=1, seed=51)
+    b = oracle.fill(k, n, kind=1, seed=52)
+    a[3, 7] = np.inf
+    b[11, 5] = np.nan
+    c, _ = _device_gemm_from_numpy(capi, gpu, a, b, np.zeros((m, n)), "ozaki")
+    assert np.all(np.isnan(c[3, :])) and np.all(np.isnan(c[:, 5]))
+    mask = np.ones((m, n), dtype=bool)
+    mask[3, :] = False
+    mask[:, 5] = False
+    a2, b2 = a.copy(), b.copy()
+    a2[3, :] = 0.0
+    b2[:, 5] = 0.0
+    assert oracle.rel_frobenius(c[mask], oracle.gemm_block(a2, b2)[mask]) <= 1e-14
