@@ -98,6 +98,15 @@ int main() {
     {1,128,128,4,4000,0},{1,128,256,2,4000,0},{1,128,256,2,4000,1},
     {2,128,128,4,4000,0},{2,128,256,2,4000,0},{2,128,256,2,4000,1},
   };
+  if (getenv("UMMA_SUSTAIN")) { /* seconds-long run of the best int8 shape: the power-capped (sustained) int8 peak */
+    Cfg c = {0, 128, 256, 2, 40000000, 0};
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0)); umma_rate_kernel<<<sms, 128, smem>>>(c, d); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("{\"kind\": \"i8\", \"M\": 128, \"N\": 256, \"K\": 32, \"sustained_seconds\": %.2f, \"chip_tops_sustained\": %.1f}\n", ms * 1e-3,
+           2.0 * 128 * 256 * 32 * (double)c.reps * sms / (ms * 1e-3) / 1e12);
+    return 0;
+  }
   for (auto &c : cfgs) {
     for (int one_sm = 0; one_sm < 2; ++one_sm) {
       const int grid = one_sm ? 1 : sms;
