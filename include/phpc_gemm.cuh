@@ -30,7 +30,11 @@ extern "C" {
  *                 reference's default 1x1) means "one per SM"; clamped to the
  *                 SM count.
  *   block_width   the reference's tile edge; accepted for CLI/CSV
- *                 compatibility, every value runs the 128x128x16 DMMA tile.
+ *                 compatibility, every value runs the same 128x128 tiles.
+ *   Kernel: the tcgen05/TMEM kernel (FP64 rebuilt exactly from int8 MMAs, see
+ *   phpc_gemm_device_ozaki in phpc_b200.h) unless the environment says
+ *   PHPC_GEMM=dmma (native-FP64 DMMA kernel).  grid_width x grid_height only
+ *   applies to the DMMA kernel.
  *   compute_time  out: device seconds of the GEMM kernel(s), mean over the local
  *                 GPUs (reference :145).
  */
