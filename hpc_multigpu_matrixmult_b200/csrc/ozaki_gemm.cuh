@@ -1,77 +1,85 @@
 /*
  * ozaki_gemm.cuh — FP64 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM).
  *
- * tcgen05.mma has no FP64 kind, so the FP64 product is rebuilt EXACTLY from integer
- * products (the Ozaki scheme): every row of A and every column of B is scaled by a
- * power of two and cut into S signed 7-bit digits (ozaki_split.cuh),
+ * tcgen05.mma has no FP64 kind, so the FP64 product is rebuilt EXACTLY from integer products (the
+ * Ozaki scheme): every row of A and every column of B is scaled by a power of two and cut into S
+ * signed 7-bit digits (ozaki_split.cuh),
  *     a_ik = 2^eA[i] * sum_t A_t[i][k] * 2^(-7t),   b_kj = 2^eB[j] * sum_u B_u[k][j] * 2^(-7u),
- * the digit matrices are multiplied on the int8 tensor pipe with exact int32
- * accumulation in TMEM (|A_t.B_u| <= K * 127^2, no rounding at all), and
+ * the digit matrices are multiplied on the int8 tensor pipe with exact int32 accumulation in TMEM
+ * (|A_t.B_u| <= K * 127^2, no rounding at all), and
  *     C[i][j] += 2^(eA[i]+eB[j]) * sum_g 2^(-7g) * P_g[i][j],   P_g = sum_{t+u=g} A_t.B_u
- * is applied in FP64 by the epilogue warps, least significant group first.  Groups with
- * g > S+1 are dropped (their weight is below 2^(-7(S+1)) of the row/column scale), so
- * S(S+1)/2 int8 MMAs stand for one FP64 MMA; S = 8 carries 56 bits.
+ * is applied in FP64 by the epilogue warps.  Groups with g > S+1 are dropped (their weight is below
+ * 2^(-7(S+1)) of the row/column scale), so S(S+1)/2 int8 MMAs stand for one FP64 MMA; S = 8 carries
+ * 56 bits.  The reference kernel this replaces is gemm_kernel of src/phpc_gemm.cu:6-57 (same
+ * C += A.B contract); the arithmetic differs from it only in the order of exact partial sums.
  *
- * Kernel (one CTA per SM, persistent over 128 x 256 output tiles, static round robin):
- *   warp 0      TMA producer: A_t tile [128 rows][128 B of k] + B_u tile [256 rows][128 B of k]
- *               per stage (both K-major, 128-byte swizzle), 4-stage mbarrier ring
- *   warp 1      TMEM allocator + MMA issuer: one lane issues tcgen05.mma.kind::i8 128x256x32,
- *               all pairs (t,u) of a group accumulate into the same TMEM accumulator;
- *               tcgen05.commit frees smem stages / publishes the accumulator
- *   warps 2-5   epilogue: tcgen05.ld the int32 accumulator (two 256-column TMEM buffers, so the
- *               epilogue of group g overlaps the MMAs of group g-1), convert, scale, C +=
- * The reference kernel this replaces is gemm_kernel of src/phpc_gemm.cu:6-57 (same C += A.B
- * contract); the arithmetic differs from it only in the order of the exact partial sums.
+ * Kernel (one CTA per SM, persistent over 128 x 128 output tiles, static round robin):
+ *   K-outer schedule  per 32-byte k step ALL needed digit tiles of A and B are staged once (one
+ *               4 KiB slot per digit matrix) and every pair (t,u) of up to four groups is issued from
+ *               them, one TMEM accumulator (128 columns) per group = all 512 TMEM columns:
+ *                 pass 1  groups S+1 .. S-2  (the 4 least significant; needs every digit)
+ *                 pass 2  groups S-3 .. 2    (digits 1..S-4 only; two k steps per stage)
+ *   digit stores  written by the split kernels ALREADY in the shared-memory order the tensor core
+ *               wants (UMMA canonical K-major, no swizzle: 8-row x 16-byte core matrices; a 128-row x
+ *               32-byte tile = 4 KiB, k chunks 128 B apart, 8-row groups 256 B apart), tile after tile:
+ *               store[row tile][k step][digit][4 KiB], so a k step of a pass is ONE contiguous global
+ *               range per operand.
+ *   warp 0      producer: two cp.async.bulk copies per k step into a 3-stage mbarrier ring
+ *   warp 1      TMEM allocator + MMA issuer: the whole warp walks warp-uniform, fully unrolled loops
+ *               and one elected lane issues tcgen05.mma.kind::i8 128x128x32 / tcgen05.commit (with the
+ *               loops inside `if (lane == 0)` every MMA cost 140-180 cycles of register -> uniform
+ *               register moves instead of 65; tools/umma_rate.cu, profiles/umma_rate*_r01.jsonl)
+ *   warps 2-5   epilogue: tcgen05.ld the four int32 accumulators of a pass, combine them exactly in
+ *               FP64 (<= 52 significant bits), transpose through shared memory, one coalesced
+ *               read-modify-write of C per pass with 32 loads in flight per lane
+ * Earlier variants (pair-outer 128x256 tiles with TMA; K-outer with 16 TMA boxes per step) and what
+ * ncu said about them are in profiles/ozaki_experiments_r01.md.
  */
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "dmma_gemm.cuh" /* mbarrier / TMA wrappers, tile_coords */
+#include "dmma_gemm.cuh" /* mbarrier wrappers, smem_u32, tile_coords */
 
 namespace phpc {
 namespace oz {
 
-constexpr int BM = 128;
-constexpr int BN = 256;
-constexpr int BKB = 128; /* bytes (= int8 elements) of k per stage: one 128-byte swizzle row */
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BKB;
-constexpr int B_BYTES = BN * BKB;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int THREADS = 192; /* warp 0 TMA, warp 1 MMA, warps 2-5 epilogue */
-constexpr int EPI_WARP_BYTES = 32 * 33 * 4; /* per epilogue warp: 32 x 32 int32 transpose tile, padded */
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * EPI_WARP_BYTES;
-constexpr int TMEM_COLS = 512; /* two int32 accumulators of 256 columns */
 constexpr int DIGIT_BITS = 7;
 constexpr int MAX_SLICES = 8;
 constexpr int ZERO_EXP = -2147483647 - 1; /* exponent of an all-zero row / column */
 constexpr int NONFINITE_EXP = 2147483647; /* the row / column holds an Inf or NaN: its C elements become NaN */
 
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BKB = 32;                /* bytes of k per step = one int8 MMA (K = 32) */
+constexpr int SLOT_BYTES = BM * BKB;   /* one digit tile: 128 rows x 32 B */
+constexpr int TILE_BYTES = SLOT_BYTES;
+constexpr int MAX_S = MAX_SLICES;
+constexpr int STAGE_BYTES = 2 * MAX_S * SLOT_BYTES; /* A digit slots then B digit slots */
+constexpr int STAGES = 3;
+constexpr int THREADS = 192;           /* warp 0 producer, warp 1 MMA, warps 2-5 epilogue */
+constexpr int EPI_WARP_BYTES = 32 * 33 * 8; /* per epilogue warp: 32 x 32 doubles, padded */
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * EPI_WARP_BYTES;
+constexpr int GROUPS_PER_PASS = 4;
+constexpr int TMEM_COLS = GROUPS_PER_PASS * BN; /* 512 */
+
 struct Params {
   double *C;
   long long ldc;
-  int M, N;    /* rows of A / C, columns of B / C (rows per digit matrix in the slice stores) */
-  int kblocks; /* padded K / 128 */
-  int S;       /* digits per operand */
+  int M, N;
+  int ksteps; /* padded K / 32 */
+  int S;      /* digits per operand */
   const int *eA;
   const int *eB;
   int tiles_m, tiles_n;
+  const int8_t *TA; /* [tiles_m][ksteps][S][4096] */
+  const int8_t *TB; /* [tiles_n][ksteps][S][4096] */
+  int prefetch;     /* k steps of L2 prefetch ahead of the shared-memory ring (0 = off) */
+  int flags;        /* diagnostics: 1 = epilogue skips the C read-modify-write, 2 = no operand loads (MMA rate only) */
 };
 
-/* UMMA shared-memory descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart */
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  /* start address, 16-byte units */
-  d |= (uint64_t)1 << 16;                   /* leading byte offset (unused for swizzled K-major) */
-  d |= (uint64_t)(1024 >> 4) << 32;         /* stride byte offset between 8-row groups */
-  d |= (uint64_t)1 << 46;                   /* descriptor version (Blackwell) */
-  d |= (uint64_t)2 << 61;                   /* layout: SWIZZLE_128B */
-  return d;
-}
-
-/* instruction descriptor: s8 x s8 -> s32, A and B K-major, M = 128, N = 256 */
+/* instruction descriptor: s8 x s8 -> s32, A and B K-major */
 __device__ __forceinline__ uint32_t idesc_i8(int m, int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
@@ -106,15 +114,6 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, int (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, int (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -132,431 +131,6 @@ __device__ __forceinline__ double pow2d(int e) {
   e = max(-1022, min(1023, e));
   return __hiloint2double((e + 1023) << 20, 0);
 }
-
-__global__ void __launch_bounds__(THREADS, 1)
-    ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES;
-  const uint32_t tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
-  const uint32_t tmem_slot = tempty0 + 16; /* 4 bytes: TMEM base address written by tcgen05.alloc */
-  const uint32_t epi0 = bars + 256;        /* transpose tiles of the epilogue warps */
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_m * p.tiles_n;
-  const int S = p.S;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull0 + 8 * b, 1);
-      mbar_init(tempty0 + 8 * b, 4); /* one arrival per epilogue warp */
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-
-  if (warp == 0) {
-    /* ===== TMA producer ===== */
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int tm, tn;
-        tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-        for (int g = S + 1; g >= 2; --g) {
-          const int t_lo = max(1, g - S), t_hi = min(S, g - 1);
-          for (int t = t_lo; t <= t_hi; ++t) {
-            const int u = g - t;
-            const int arow = (t - 1) * p.M + tm * BM;
-            const int brow = (u - 1) * p.N + tn * BN;
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-              mbar_wait(empty0 + 8 * stage, phase ^ 1);
-              const uint32_t full = full0 + 8 * stage;
-              mbar_expect_tx(full, STAGE_BYTES);
-              const uint32_t sa = smem_base + stage * STAGE_BYTES;
-              tma_load_2d(sa, &tmA, full, kb * BKB, arow);
-              tma_load_2d(sa + A_BYTES, &tmB, full, kb * BKB, brow);
-              if (++stage == STAGES) {
-                stage = 0;
-                phase ^= 1;
-              }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    /* ===== MMA issuer: one lane, accumulators in TMEM ===== */
-    if (lane == 0) {
-      const uint32_t idesc = idesc_i8(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t unit = 0; /* counts (tile, group) units: TMEM buffer = unit & 1 */
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int g = S + 1; g >= 2; --g, ++unit) {
-          const uint32_t buf = unit & 1;
-          mbar_wait(tempty0 + 8 * buf, ((unit >> 1) & 1) ^ 1); /* epilogue drained this buffer */
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t tacc = tmem_base + buf * BN;
-          const int pairs = min(S, g - 1) - max(1, g - S) + 1;
-          uint32_t accumulate = 0;
-          for (int it = 0; it < pairs * p.kblocks; ++it) {
-            mbar_wait(full0 + 8 * stage, phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + A_BYTES);
-#pragma unroll
-            for (int kk = 0; kk < BKB / 32; ++kk) {
-              umma_i8(tacc, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, accumulate); /* +32 bytes of k */
-              accumulate = 1;
-            }
-            umma_commit(empty0 + 8 * stage); /* smem stage reusable once these MMAs retire */
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-          umma_commit(tfull0 + 8 * buf); /* accumulator of this group complete */
-        }
-      }
-    }
-  } else {
-    /* ===== epilogue: 4 warps, warp w reads TMEM lanes 32*(w%4) .. +31 =====
-     * tcgen05.ld hands every thread one ROW of the accumulator; a 32x32 int32 block is turned
-     * through shared memory so that the C read-modify-write is done with lanes along a row
-     * (256 contiguous bytes per warp access). */
-    const int quarter = warp & 3;
-    const uint32_t tr = epi0 + (uint32_t)(warp - 2) * EPI_WARP_BYTES; /* this warp's 32 x 33 int32 transpose tile */
-    uint32_t unit = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int tm, tn;
-      tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-      const int row0 = tm * BM + quarter * 32;
-      const int my_row = row0 + lane;
-      const int ea = (my_row < p.M) ? p.eA[my_row] : ZERO_EXP; /* lane r holds the exponent of row row0 + r */
-      const int rows_here = min(32, p.M - row0);               /* <= 0: nothing of this warp's rows is inside C */
-      for (int g = S + 1; g >= 2; --g, ++unit) {
-        const uint32_t buf = unit & 1;
-        mbar_wait(tfull0 + 8 * buf, (unit >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          const int col = tn * BN + c0 + lane; /* the column this lane owns after the transpose */
-          if (tn * BN + c0 >= p.N || rows_here <= 0) break;
-          int v[32];
-          tmem_ld_32x32b_x32(taddr + c0, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 32; ++j) asm volatile("st.shared.b32 [%0], %1;" ::"r"(tr + (uint32_t)(lane * 33 + j) * 4), "r"(v[j]) : "memory");
-          __syncwarp();
-          const int eb = (col < p.N) ? __ldg(p.eB + col) : ZERO_EXP;
-          double *cptr = p.C + (long long)row0 * p.ldc + col;
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            int x;
-            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(x) : "r"(tr + (uint32_t)(rr * 33 + lane) * 4) : "memory");
-            const int er = __shfl_sync(0xffffffffu, ea, rr);
-            if (rr < rows_here && eb != ZERO_EXP && er != ZERO_EXP && x != 0)
-              cptr[(long long)rr * p.ldc] += (double)x * pow2d(er + eb - DIGIT_BITS * g); /* exact product, one rounding */
-          }
-          __syncwarp();
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
-      }
-    }
-  }
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
-}
-
-}  // namespace oz
-}  // namespace phpc
-
-/* =====================================================================================
- * Version 2: K-outer schedule.  v1 walks the pairs (t,u) in the outer loop and streams a
- * fresh A_t and B_u tile for every MMA group, i.e. 96 bytes of operands per SM-cycle of tensor
- * work — ncu shows it memory-system bound (profiles/ncu_ozaki_gemm_n8192_r01_v1.txt).
- * v2 turns the loops around: per 32-byte k step ALL needed digit tiles of A and B are staged
- * once (one 4 KiB slot per digit matrix, 32-byte swizzle) and every pair (t,u) of up to four
- * groups is issued from them, with one TMEM accumulator (128 columns) per group:
- *   pass 1  groups S+1 .. S-2   (the 4 least significant; needs every digit)
- *   pass 2  groups S-3 .. 2     (digits 1..S-4 only)
- * Operand traffic drops to ~40 bytes per SM-cycle, and the epilogue combines the four groups of
- * a pass exactly in FP64 (<= 52 significant bits) before ONE read-modify-write of C.
- * ===================================================================================== */
-namespace phpc {
-namespace oz2 {
-
-using oz::DIGIT_BITS;
-using oz::ZERO_EXP;
-
-constexpr int BM = 128;
-constexpr int BN = 128;
-constexpr int BKB = 32;                /* bytes of k per stage = one int8 MMA (K = 32) */
-constexpr int SLOT_BYTES = BM * BKB;   /* one digit tile: 128 rows x 32 B */
-constexpr int MAX_S = 8;
-constexpr int STAGE_BYTES = 2 * MAX_S * SLOT_BYTES; /* A digits then B digits */
-constexpr int STAGES = 3;
-constexpr int THREADS = 192;
-constexpr int EPI_WARP_BYTES = 32 * 33 * 8; /* 32 x 32 doubles, padded */
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * EPI_WARP_BYTES;
-constexpr int GROUPS_PER_PASS = 4;
-constexpr int TMEM_COLS = GROUPS_PER_PASS * BN; /* 512 */
-
-struct Params {
-  double *C;
-  long long ldc;
-  int M, N;
-  int ksteps; /* padded K / 32 */
-  int S;
-  const int *eA;
-  const int *eB;
-  int tiles_m, tiles_n;
-};
-
-/* K-major, 32-byte swizzle: 8-row atoms of 256 bytes */
-__device__ __forceinline__ uint64_t smem_desc_sw32(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(256 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)6 << 61; /* SWIZZLE_32B */
-  return d;
-}
-
-__global__ void __launch_bounds__(THREADS, 1)
-    ozaki_gemm_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  extern __shared__ unsigned char smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
-  const uint32_t full0 = bars, empty0 = bars + 8 * STAGES;
-  const uint32_t tfull = bars + 16 * STAGES, tempty = tfull + 8;
-  const uint32_t tmem_slot = tempty + 8;
-  const uint32_t epi0 = bars + 256;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_m * p.tiles_n;
-  const int S = p.S;
-  const int npass = (S + GROUPS_PER_PASS - 1) / GROUPS_PER_PASS; /* S groups (g = 2 .. S+1) */
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
-    }
-    mbar_init(tfull, 1);
-    mbar_init(tempty, 4);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
-
-  if (warp == 0) {
-    /* ===== TMA producer: per k step, one 4 KiB tile per needed digit matrix of A and of B ===== */
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int tm, tn;
-        tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-        for (int ps = 0; ps < npass; ++ps) {
-          const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
-          const int d_hi = min(S, g_hi - 1); /* digits 1 .. d_hi take part in this pass */
-          for (int ks = 0; ks < p.ksteps; ++ks) {
-            mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            const uint32_t full = full0 + 8 * stage;
-            mbar_expect_tx(full, 2 * d_hi * SLOT_BYTES);
-            const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            for (int t = 1; t <= d_hi; ++t) {
-              tma_load_2d(sa + (t - 1) * SLOT_BYTES, &tmA, full, ks * BKB, (t - 1) * p.M + tm * BM);
-              tma_load_2d(sa + (MAX_S + t - 1) * SLOT_BYTES, &tmB, full, ks * BKB, (t - 1) * p.N + tn * BN);
-            }
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    /* ===== MMA issuer ===== */
-    if (lane == 0) {
-      const uint32_t idesc = oz::idesc_i8(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t unit = 0; /* (tile, pass) counter */
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int ps = 0; ps < npass; ++ps, ++unit) {
-          const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
-          const int g_lo = max(2, g_hi - GROUPS_PER_PASS + 1);
-          mbar_wait(tempty, (unit & 1) ^ 1); /* epilogue drained the accumulators of the previous pass */
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          for (int ks = 0; ks < p.ksteps; ++ks) {
-            mbar_wait(full0 + 8 * stage, phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            for (int g = g_hi; g >= g_lo; --g) {
-              const uint32_t tacc = tmem_base + (uint32_t)(g - g_lo) * BN;
-              const int t_lo = max(1, g - S), t_hi = min(S, g - 1);
-              for (int t = t_lo; t <= t_hi; ++t) {
-                const int u = g - t;
-                oz::umma_i8(tacc, smem_desc_sw32(sa + (t - 1) * SLOT_BYTES), smem_desc_sw32(sa + (MAX_S + u - 1) * SLOT_BYTES), idesc,
-                            (ks > 0 || t > t_lo) ? 1u : 0u);
-              }
-            }
-            oz::umma_commit(empty0 + 8 * stage);
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-          oz::umma_commit(tfull);
-        }
-      }
-    }
-  } else {
-    /* ===== epilogue: combine the groups of a pass exactly, then one C += per element ===== */
-    const int quarter = warp & 3;
-    const uint32_t tr = epi0 + (uint32_t)(warp - 2) * EPI_WARP_BYTES;
-    uint32_t unit = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int tm, tn;
-      tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-      const int row0 = tm * BM + quarter * 32;
-      const int my_row = row0 + lane;
-      const int ea = (my_row < p.M) ? p.eA[my_row] : ZERO_EXP;
-      const int rows_here = min(32, p.M - row0);
-      for (int ps = 0; ps < npass; ++ps, ++unit) {
-        const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
-        const int g_lo = max(2, g_hi - GROUPS_PER_PASS + 1);
-        mbar_wait(tfull, unit & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          if (tn * BN + c0 >= p.N || rows_here <= 0) break;
-          double acc[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-          for (int g = g_hi; g >= g_lo; --g) { /* least significant group first; every partial sum is exact */
-            int v[32];
-            oz::tmem_ld_32x32b_x32(tlane + (uint32_t)(g - g_lo) * BN + c0, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const double w = oz::pow2d(DIGIT_BITS * (g_hi - g)); /* relative weight inside the pass: 2^(7(g_hi-g)) */
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            asm volatile("st.shared.f64 [%0], %1;" ::"r"(tr + (uint32_t)(lane * 33 + j) * 8), "d"(acc[j]) : "memory");
-          __syncwarp();
-          const int col = tn * BN + c0 + lane;
-          const int eb = (col < p.N) ? __ldg(p.eB + col) : ZERO_EXP;
-          double *cptr = p.C + (long long)row0 * p.ldc + col;
-#pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) {
-            double x;
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(tr + (uint32_t)(rr * 33 + lane) * 8) : "memory");
-            const int er = __shfl_sync(0xffffffffu, ea, rr);
-            if (rr < rows_here && eb != ZERO_EXP && er != ZERO_EXP && x != 0.0)
-              cptr[(long long)rr * p.ldc] += x * oz::pow2d(er + eb - DIGIT_BITS * g_hi);
-          }
-          __syncwarp();
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty);
-      }
-    }
-  }
-
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-  }
-}
-
-}  // namespace oz2
-}  // namespace phpc
-
-/* =====================================================================================
- * Version 3: v2's K-outer schedule fed by 1-D bulk copies.  ncu on v2 shows the tensor pipe only
- * 43 % busy with DRAM and L2 far from saturated (profiles/ncu_ozaki_gemm_n8192_r01_v2.txt): a
- * k step needs 16 TMA boxes of 128 rows x 32 B, i.e. 2048 separate 32-byte rows, and the TMA
- * row rate, not bandwidth, paces the pipeline.  The split kernels therefore emit the digits
- * ALREADY in the shared-memory order the tensor core wants (UMMA canonical K-major, no swizzle:
- * 8-row x 16-byte core matrices; 128-row x 32-byte tile = 4 KiB, k chunks 128 B apart, 8-row groups
- * 256 B apart), tile after tile:
- *     store[row tile][k step][digit][4 KiB tile]
- * so one k step of a pass is ONE contiguous global range per operand (digits 1..d are the first
- * d tiles) and the producer issues two cp.async.bulk copies instead of 16 tensor copies.
- * ===================================================================================== */
-namespace phpc {
-namespace oz3 {
-
-using oz::DIGIT_BITS;
-using oz::ZERO_EXP;
-/* same tile shape, stages and TMEM use as v2 */
-constexpr int BM = oz2::BM, BN = oz2::BN, SLOT_BYTES = oz2::SLOT_BYTES, MAX_S = oz2::MAX_S, STAGE_BYTES = oz2::STAGE_BYTES;
-constexpr int STAGES = oz2::STAGES, THREADS = oz2::THREADS, EPI_WARP_BYTES = oz2::EPI_WARP_BYTES, SMEM_BYTES = oz2::SMEM_BYTES;
-constexpr int GROUPS_PER_PASS = oz2::GROUPS_PER_PASS, TMEM_COLS = oz2::TMEM_COLS;
-
-constexpr int TILE_BYTES = SLOT_BYTES; /* 4096 */
-
-struct Params3 {
-  double *C;
-  long long ldc;
-  int M, N;
-  int ksteps;
-  int S;
-  const int *eA;
-  const int *eB;
-  int tiles_m, tiles_n;
-  const int8_t *TA; /* [tiles_m][ksteps][S][4096] */
-  const int8_t *TB; /* [tiles_n][ksteps][S][4096] */
-  int prefetch;     /* k steps of L2 prefetch ahead of the shared-memory ring (0 = off) */
-  int flags;        /* diagnostics: 1 = epilogue skips the C read-modify-write, 2 = no operand loads (MMA rate only) */
-};
 
 /* byte offset of element (row r < 128, k byte kb < 32) inside a canonical 4 KiB tile */
 __host__ __device__ __forceinline__ int tile_offset(int r, int kb) { return (r >> 3) * 256 + (kb >> 4) * 128 + (r & 7) * 16 + (kb & 15); }
@@ -578,7 +152,7 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
 }
 
 template <int S_T>
-__global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3 p) {
+__global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
@@ -658,7 +232,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
      * elected lane issues tcgen05.mma / tcgen05.commit.  With the loops inside `if (lane == 0)` every
      * MMA cost ~140-180 cycles of register->uniform-register traffic (tools/umma_rate.cu). ===== */
     {
-      const uint32_t idesc = oz::idesc_i8(BM, BN);
+      const uint32_t idesc = idesc_i8(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t unit = 0;
@@ -675,7 +249,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
             if (!(p.flags & 2)) mbar_wait(full0 + 8 * stage, phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            if (oz::elect_one()) {
+            if (elect_one()) {
               for (int h = 0; h < nsub; ++h) {
                 const uint64_t da0 = smem_desc_kmajor_noswz(sa + h * d_hi * SLOT_BYTES);
                 const uint64_t db0 = smem_desc_kmajor_noswz(sa + (MAX_S + h * d_hi) * SLOT_BYTES);
@@ -689,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
                       const int g = g_hi - gi;
                       const int u = g - t;
                       if (g >= g_lo && t <= S && u >= 1 && u <= S)
-                        oz::umma_i8(tmem_base + (uint32_t)(g - g_lo) * BN, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)),
+                        umma_i8(tmem_base + (uint32_t)(g - g_lo) * BN, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)),
                                     db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc, (t > max(1, g - S)) ? 1u : first);
                     }
                   }
@@ -699,13 +273,13 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
                     const int t_lo = max(1, g - S), t_hi = min(S, g - 1);
                     for (int t = t_lo; t <= t_hi; ++t) {
                       const int u = g - t;
-                      oz::umma_i8(tacc, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)), db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc,
+                      umma_i8(tacc, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)), db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc,
                                   (t > t_lo) ? 1u : first);
                     }
                   }
                 }
               }
-              if (!(p.flags & 2)) oz::umma_commit(empty0 + 8 * stage);
+              if (!(p.flags & 2)) umma_commit(empty0 + 8 * stage);
             }
             __syncwarp();
             if (++stage == STAGES) {
@@ -713,13 +287,13 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
               phase ^= 1;
             }
           }
-          if (oz::elect_one()) oz::umma_commit(tfull);
+          if (elect_one()) umma_commit(tfull);
           __syncwarp();
         }
       }
     }
   } else {
-    /* ===== epilogue (as v2) ===== */
+    /* ===== epilogue: combine the groups of a pass exactly, then one C += per element ===== */
     const int quarter = warp & 3;
     const uint32_t tr = epi0 + (uint32_t)(warp - 2) * EPI_WARP_BYTES;
     uint32_t unit = 0;
@@ -744,9 +318,9 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
           for (int j = 0; j < 32; ++j) acc[j] = 0.0;
           for (int g = g_hi; g >= g_lo; --g) {
             int v[32];
-            oz::tmem_ld_32x32b_x32(tlane + (uint32_t)(g - g_lo) * BN + c0, v);
+            tmem_ld_32x32b_x32(tlane + (uint32_t)(g - g_lo) * BN + c0, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const double w = oz::pow2d(DIGIT_BITS * (g_hi - g));
+            const double w = pow2d(DIGIT_BITS * (g_hi - g));
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]);
           }
@@ -769,10 +343,10 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
             asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(tr + (uint32_t)(rr * 33 + lane) * 8) : "memory");
             const int er = __shfl_sync(0xffffffffu, ea, rr);
             if (col_ok && rr < rows_here) {
-              if (er == oz::NONFINITE_EXP || eb == oz::NONFINITE_EXP)
+              if (er == NONFINITE_EXP || eb == NONFINITE_EXP)
                 cptr[(long long)rr * p.ldc] = __longlong_as_double(0x7ff8000000000000ll); /* Inf/NaN in the row or column */
               else if (er != ZERO_EXP && x != 0.0)
-                cptr[(long long)rr * p.ldc] = cold[rr] + x * oz::pow2d(er + eb - DIGIT_BITS * g_hi);
+                cptr[(long long)rr * p.ldc] = cold[rr] + x * pow2d(er + eb - DIGIT_BITS * g_hi);
             }
           }
           __syncwarp();
@@ -792,5 +366,6 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel_v3(const Params3
   }
 }
 
-}  // namespace oz3
+
+}  // namespace oz
 }  // namespace phpc

@@ -60,78 +60,7 @@ __global__ void col_exp_kernel(const double *__restrict__ B, long long ldb, int 
   if (e != ZERO_EXP) atomicMax(eB + col, e);
 }
 
-__device__ __forceinline__ double scale_pow2(double x, int minus_e) { /* x * 2^-e, exact for normal results */
-  return scalbn(x, -minus_e);
-}
-
-/* A digits: thread = 16 consecutive k of one row -> one 16-byte store per digit matrix. */
-__global__ void split_a_kernel(const double *__restrict__ A, long long lda, int m, int k, int kp, const int *__restrict__ eA,
-                               int8_t *__restrict__ SA, int S) {
-  const int chunks = kp / 16;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)m * chunks) return;
-  const int row = (int)(idx / chunks), c0 = (int)(idx % chunks) * 16;
-  const int e = eA[row];
-  double r[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    const int c = c0 + j;
-    r[j] = (c < k && e != ZERO_EXP) ? scale_pow2(A[(long long)row * lda + c], e) : 0.0;
-  }
-  for (int t = 0; t < S; ++t) {
-    union {
-      int8_t b[16];
-      int4 v;
-    } out;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const double s = r[j] * 128.0;
-      const int d = (int)s; /* truncation toward zero */
-      r[j] = s - (double)d;
-      out.b[j] = (int8_t)d;
-    }
-    *reinterpret_cast<int4 *>(SA + ((long long)t * m + row) * kp + c0) = out.v;
-  }
-}
-
-/* B digits, transposed to K-major: thread = 32 consecutive k of one column (warp = 32 adjacent
- * columns, so every B row read is a coalesced 256-byte line) -> one 32-byte sector per digit. */
-__global__ void split_b_kernel(const double *__restrict__ B, long long ldb, int k, int n, int kp, const int *__restrict__ eB,
-                               int8_t *__restrict__ SB, int S) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  const int k0 = blockIdx.y * 32;
-  if (col >= n) return;
-  const int e = eB[col];
-  double r[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int row = k0 + j;
-    r[j] = (row < k && e != ZERO_EXP) ? scale_pow2(B[(long long)row * ldb + col], e) : 0.0;
-  }
-  for (int t = 0; t < S; ++t) {
-    union {
-      int8_t b[32];
-      int4 v[2];
-    } out;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const double s = r[j] * 128.0;
-      const int d = (int)s;
-      r[j] = s - (double)d;
-      out.b[j] = (int8_t)d;
-    }
-    int4 *dst = reinterpret_cast<int4 *>(SB + ((long long)t * n + col) * kp + k0);
-    dst[0] = out.v[0];
-    dst[1] = out.v[1];
-  }
-}
-
-}  // namespace oz
-}  // namespace phpc
-
-/* ---- tiled digit stores for ozaki_gemm_kernel_v3: store[row tile][k step][digit][4 KiB canonical tile] ---- */
-namespace phpc {
-namespace oz3 {
+/* ---- tiled digit stores: store[row tile][k step][digit][4 KiB canonical tile] ---- */
 
 /* A: thread = 16 consecutive k of one (padded) row = one 16-byte chunk of a core matrix per digit */
 __global__ void split_a_tiled_kernel(const double *__restrict__ A, long long lda, int m, int k, int kp, const int *__restrict__ eA,
@@ -143,12 +72,12 @@ __global__ void split_a_tiled_kernel(const double *__restrict__ A, long long lda
   /* consecutive threads walk down the rows of one k chunk: the 8 rows of a core matrix are 128 contiguous bytes */
   const int chunk = (int)(idx / m_pad), row = (int)(idx % m_pad);
   const int c0 = chunk * 16;
-  const int e = row < m ? eA[row] : oz::ZERO_EXP;
+  const int e = row < m ? eA[row] : ZERO_EXP;
   double r[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int c = c0 + j;
-    r[j] = (row < m && c < k && e != oz::ZERO_EXP && e != oz::NONFINITE_EXP) ? scalbn(A[(long long)row * lda + c], -e) : 0.0;
+    r[j] = (row < m && c < k && e != ZERO_EXP && e != NONFINITE_EXP) ? scalbn(A[(long long)row * lda + c], -e) : 0.0;
   }
   const int ksteps = kp / 32;
   const size_t base = (((size_t)(row >> 7) * ksteps + (c0 >> 5)) * S) * 4096 + tile_offset(row & 127, c0 & 31);
@@ -176,12 +105,12 @@ __global__ void split_b_tiled_kernel(const double *__restrict__ B, long long ldb
   if (col >= n_pad) return;
   const int ks = blockIdx.y; /* k step of 32 */
   const int k0 = ks * 32;
-  const int e = col < n ? eB[col] : oz::ZERO_EXP;
+  const int e = col < n ? eB[col] : ZERO_EXP;
   double r[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const int row = k0 + j;
-    r[j] = (col < n && row < k && e != oz::ZERO_EXP && e != oz::NONFINITE_EXP) ? scalbn(B[(long long)row * ldb + col], -e) : 0.0;
+    r[j] = (col < n && row < k && e != ZERO_EXP && e != NONFINITE_EXP) ? scalbn(B[(long long)row * ldb + col], -e) : 0.0;
   }
   const int ksteps = kp / 32;
   const size_t base = (((size_t)(col >> 7) * ksteps + ks) * S) * 4096 + tile_offset(col & 127, 0);
@@ -203,5 +132,6 @@ __global__ void split_b_tiled_kernel(const double *__restrict__ B, long long ldb
   }
 }
 
-}  // namespace oz3
+
+}  // namespace oz
 }  // namespace phpc

@@ -32,9 +32,6 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static encode_tiled_fn g_encode_tiled = nullptr;
-typedef CUresult (*addr_range_fn)(CUdeviceptr *, size_t *, CUdeviceptr);
-static addr_range_fn g_addr_range = nullptr;
-
 static void load_driver_entry_points() {
   if (g_encode_tiled) return;
   void *fn = nullptr;
@@ -42,19 +39,6 @@ static void load_driver_entry_points() {
   CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   PHPC_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "driver has no cuTensorMapEncodeTiled (need CUDA 12+ driver)");
   g_encode_tiled = (encode_tiled_fn)fn;
-  fn = nullptr;
-  CUDA_CHECK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
-  PHPC_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "driver has no cuMemGetAddressRange");
-  g_addr_range = (addr_range_fn)fn;
-}
-
-long long phpc_offset_in_allocation(const void *dptr) {
-  load_driver_entry_points();
-  CUdeviceptr base = 0;
-  size_t size = 0;
-  CUresult r = g_addr_range(&base, &size, (CUdeviceptr)dptr);
-  if (r != CUDA_SUCCESS) phpc_die("cuMemGetAddressRange", "not a device allocation", __FILE__, __LINE__);
-  return (long long)((CUdeviceptr)dptr - base);
 }
 
 DeviceCtx *phpc_ctx(int device) {
@@ -85,10 +69,8 @@ DeviceCtx *phpc_ctx(int device) {
   CUDA_CHECK(cudaEventCreate(&ctx->ev0));
   CUDA_CHECK(cudaEventCreate(&ctx->ev1));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::GEMM_SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz2::ozaki_gemm_kernel_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz2::SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz3::ozaki_gemm_kernel_v3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz2::SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz3::ozaki_gemm_kernel_v3<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz2::SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
   load_driver_entry_points();
   ctx->ready = true;
   return ctx;
@@ -253,21 +235,6 @@ int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const doub
 /* ------------------------------------------------------------------------- */
 /* Ozaki (int8 tcgen05) launcher                                              */
 /* ------------------------------------------------------------------------- */
-static void encode_map_bytes(CUtensorMap *map, const void *base, long long inner_bytes, long long outer, int box_inner, int box_outer,
-                             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
-  cuuint64_t gdim[2] = {(cuuint64_t)inner_bytes, (cuuint64_t)outer};
-  cuuint64_t gstride[1] = {(cuuint64_t)inner_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-  cuuint32_t estride[2] = {1, 1};
-  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    char msg[160];
-    snprintf(msg, sizeof msg, "CUresult %d (digit matrix %lld x %lld bytes)", (int)r, outer, inner_bytes);
-    phpc_die("cuTensorMapEncodeTiled", msg, __FILE__, __LINE__);
-  }
-}
-
 int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                       int k, int n, int slices, cudaStream_t stream) {
   using namespace phpc::oz;
@@ -281,18 +248,16 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
   /* int32 accumulation of a whole group is exact while  K * S * 127^2 < 2^31  (S = 8: K <= 16643) */
   const int kc_max = 8192;
   int launches = 0;
-  const char *kv = getenv("PHPC_OZAKI_KERNEL");
-  const int version = (kv && *kv) ? atoi(kv) : 3; /* 1 = pair-outer 128x256 tiles (TMA), 2 = K-outer 128x128 (TMA), 3 = K-outer, pre-tiled + bulk copies */
-  const int bn = version == 1 ? BN : phpc::oz2::BN;
-  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + bn - 1) / bn;
+  const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
   const long long tiles = (long long)tiles_m * tiles_n;
-  PHPC_REQUIRE(tiles < (1ll << 30) && (long long)slices * m < (1ll << 31) && (long long)slices * n < (1ll << 31), "problem too large");
+  PHPC_REQUIRE(tiles < (1ll << 30), "too many output tiles");
+  const size_t m_pad = (size_t)tiles_m * BM, n_pad = (size_t)tiles_n * BN;
+  const char *pf = getenv("PHPC_OZ_PF"), *fl = getenv("PHPC_OZ_FLAGS"); /* diagnostics, see profiles/ozaki_experiments_r01.md */
   for (int k0 = 0; k0 < k; k0 += kc_max) {
     const int kc = (k - k0 < kc_max) ? k - k0 : kc_max;
-    const int kp = (kc + BKB - 1) / BKB * BKB;
-    const size_t m_pad = (size_t)tiles_m * BM, n_pad = (size_t)tiles_n * bn;
-    int8_t *SA = (int8_t *)phpc_buf_reserve(&ctx->ozA, (size_t)slices * (version == 3 ? m_pad : (size_t)m) * kp);
-    int8_t *SB = (int8_t *)phpc_buf_reserve(&ctx->ozB, (size_t)slices * (version == 3 ? n_pad : (size_t)n) * kp);
+    const int kp = (kc + 127) / 128 * 128;
+    int8_t *TA = (int8_t *)phpc_buf_reserve(&ctx->ozA, (size_t)slices * m_pad * kp);
+    int8_t *TB = (int8_t *)phpc_buf_reserve(&ctx->ozB, (size_t)slices * n_pad * kp);
     int *eA = (int *)phpc_buf_reserve(&ctx->ozE, ((size_t)m + n) * sizeof(int));
     int *eB = eA + m;
     const double *a = dA + k0;
@@ -305,74 +270,33 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
       dim3 grid((n + 255) / 256, (kc + 63) / 64);
       col_exp_kernel<<<grid, 256, 0, stream>>>(b, ldb, kc, n, eB);
     }
-    if (version == 3) {
+    {
       const long long threads = (long long)m_pad * (kp / 16);
-      phpc::oz3::split_a_tiled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, SA, slices);
+      split_a_tiled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, TA, slices);
       dim3 grid((unsigned)((n_pad + 127) / 128), kp / 32);
-      phpc::oz3::split_b_tiled_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, SB, slices);
-    } else {
-      const long long threads = (long long)m * (kp / 16);
-      split_a_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, SA, slices);
-      dim3 grid((n + 127) / 128, kp / 32);
-      split_b_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, SB, slices);
+      split_b_tiled_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, TB, slices);
     }
-    CUtensorMap tmA, tmB;
+    Params p;
+    p.C = dC;
+    p.ldc = ldc;
+    p.M = m;
+    p.N = n;
+    p.ksteps = kp / BKB;
+    p.S = slices;
+    p.eA = eA;
+    p.eB = eB;
+    p.tiles_m = tiles_m;
+    p.tiles_n = tiles_n;
+    p.TA = TA;
+    p.TB = TB;
+    p.prefetch = (pf && *pf) ? atoi(pf) : 0;
+    p.flags = (fl && *fl) ? atoi(fl) : 0;
     int grid = ctx->sm_count;
     if ((long long)grid > tiles) grid = (int)tiles;
-    if (version == 3) {
-      namespace v3 = phpc::oz3;
-      v3::Params3 p;
-      p.C = dC;
-      p.ldc = ldc;
-      p.M = m;
-      p.N = n;
-      p.ksteps = kp / 32;
-      p.S = slices;
-      p.eA = eA;
-      p.eB = eB;
-      p.tiles_m = tiles_m;
-      p.tiles_n = tiles_n;
-      p.TA = SA;
-      p.TB = SB;
-      const char *pf = getenv("PHPC_OZ_PF"), *fl = getenv("PHPC_OZ_FLAGS");
-      p.prefetch = (pf && *pf) ? atoi(pf) : 0; /* measured: no gain (profiles/ozaki_experiments_r01.md) */
-      p.flags = (fl && *fl) ? atoi(fl) : 0;
-      if (slices == 8)
-        v3::ozaki_gemm_kernel_v3<8><<<grid, phpc::oz2::THREADS, phpc::oz2::SMEM_BYTES, stream>>>(p);
-      else
-        v3::ozaki_gemm_kernel_v3<0><<<grid, phpc::oz2::THREADS, phpc::oz2::SMEM_BYTES, stream>>>(p);
-    } else if (version == 1) {
-      encode_map_bytes(&tmA, SA, kp, (long long)slices * m, BKB, BM);
-      encode_map_bytes(&tmB, SB, kp, (long long)slices * n, BKB, BN);
-      Params p;
-      p.C = dC;
-      p.ldc = ldc;
-      p.M = m;
-      p.N = n;
-      p.kblocks = kp / BKB;
-      p.S = slices;
-      p.eA = eA;
-      p.eB = eB;
-      p.tiles_m = tiles_m;
-      p.tiles_n = tiles_n;
-      ozaki_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
-    } else {
-      namespace v2 = phpc::oz2;
-      encode_map_bytes(&tmA, SA, kp, (long long)slices * m, v2::BKB, v2::BM, CU_TENSOR_MAP_SWIZZLE_32B);
-      encode_map_bytes(&tmB, SB, kp, (long long)slices * n, v2::BKB, v2::BN, CU_TENSOR_MAP_SWIZZLE_32B);
-      v2::Params p;
-      p.C = dC;
-      p.ldc = ldc;
-      p.M = m;
-      p.N = n;
-      p.ksteps = kp / v2::BKB;
-      p.S = slices;
-      p.eA = eA;
-      p.eB = eB;
-      p.tiles_m = tiles_m;
-      p.tiles_n = tiles_n;
-      v2::ozaki_gemm_kernel_v2<<<grid, v2::THREADS, v2::SMEM_BYTES, stream>>>(tmA, tmB, p);
-    }
+    if (slices == 8)
+      ozaki_gemm_kernel<8><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
+    else
+      ozaki_gemm_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
     CUDA_CHECK(cudaGetLastError());
     launches += 6;
   }

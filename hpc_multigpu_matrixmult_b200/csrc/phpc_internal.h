@@ -69,7 +69,4 @@ bool phpc_use_ozaki(void); /* env PHPC_GEMM=ozaki */
 void phpc_launch_cublas(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                         int k, int n, cudaStream_t stream);
 
-/* byte offset of a device pointer inside the cudaMalloc allocation that contains it */
-long long phpc_offset_in_allocation(const void *dptr);
-
 static inline long long phpc_pad_ld(long long cols) { return (cols + 15) / 16 * 16; }

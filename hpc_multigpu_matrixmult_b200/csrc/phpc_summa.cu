@@ -50,22 +50,6 @@ static double now_s() {
     if (getenv("PHPC_DEBUG")) fprintf(stderr, "[phpc %d] %-28s %.3f s\n", rank, what, now_s() - (t0)); \
   } while (0)
 
-__global__ void debug_sum_kernel(const double *p, size_t n, double *out) {
-  double acc = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += p[i];
-  atomicAdd(out, acc);
-}
-static double debug_sum(const double *p, size_t n, cudaStream_t st) {
-  double *d, h = 0;
-  cudaMalloc(&d, 8);
-  cudaMemsetAsync(d, 0, 8, st);
-  debug_sum_kernel<<<64, 256, 0, st>>>(p, n, d);
-  cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, st);
-  cudaStreamSynchronize(st);
-  cudaFree(d);
-  return h;
-}
-
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
@@ -310,11 +294,6 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
     for (int root = 0; root < s->size; ++root) MPI_Bcast(&all[root], (int)sizeof(Handles), MPI_BYTE, root, grid_comm);
     s->peerA.assign(s->c, nullptr);
     s->peerB.assign(s->r, nullptr);
-    if (getenv("PHPC_DEBUG_SUMS")) {
-      const unsigned long long *w = (const unsigned long long *)&all[s->rank].a;
-      fprintf(stderr, "[phpc %d] export dA=%p handle=%016llx %016llx %016llx %016llx alloc_off=%lld\n", s->rank, (void *)s->dA, w[0], w[1],
-              w[2], w[3], phpc_offset_in_allocation(s->dA));
-    }
     s->peerA_base.assign(s->c, nullptr);
     s->peerB_base.assign(s->r, nullptr);
     for (int pj2 = 0; pj2 < s->c; ++pj2)
@@ -325,11 +304,6 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
         unsigned long long seen = 0;
         CUDA_CHECK(cudaMemcpy(&seen, (char *)s->peerA_base[pj2] + h.a_tag_off, 8, cudaMemcpyDeviceToHost));
         PHPC_REQUIRE(seen == h.a_tag, "CUDA IPC mapping of a peer's A store does not show the peer's tag");
-        if (getenv("PHPC_DEBUG_SUMS")) {
-          const unsigned long long *w = (const unsigned long long *)&h.a;
-          fprintf(stderr, "[phpc %d] import from col %d handle=%016llx %016llx %016llx %016llx -> %p\n", s->rank, pj2, w[0], w[1], w[2], w[3],
-                  s->peerA_base[pj2]);
-        }
       }
     for (int pi2 = 0; pi2 < s->r; ++pi2)
       if (pi2 != s->pi) {
@@ -612,12 +586,6 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
     }
     CUDA_CHECK(cudaEventRecord(s->ev_g1[q], comp));
     if (any_comm) CUDA_CHECK(cudaEventRecord(s->ev_free[slot], comp));
-    if (getenv("PHPC_DEBUG_SUMS")) { /* serialising diagnostic: what did this step multiply? */
-      CUDA_CHECK(cudaDeviceSynchronize());
-      const double sa = debug_sum(a, (size_t)s->m * lda, comp), sb = debug_sum(b, (size_t)st.width * s->ldn, comp);
-      fprintf(stderr, "[phpc %d] step %d own_a=%d own_b=%d slot=%d a=%p sumA=%.6e sumB=%.6e root_a_off=%lld\n", s->rank, q, st.own_a,
-              st.own_b, slot, (const void *)a, sa, sb, s->root_a_off[q]);
-    }
     /* prefetch: the stage-in of the next nbuf-1 steps runs under this GEMM */
     while (issued < nsteps && issued < q + s->nbuf) stage_in(issued++);
   }
