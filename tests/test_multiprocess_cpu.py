@@ -50,3 +50,32 @@ def test_mpirun_propagates_failure_and_rank_env(built, tmp_path):
     assert sorted(out.stdout.split()) == ["0/3", "1/3", "2/3"]
     bad = subprocess.run([mpirun, "-n", "2", "sh", "-c", "exit 7"], capture_output=True, text=True, timeout=60)
     assert bad.returncode == 7
+
+
+@pytest.mark.parametrize("ranks", [1, 2, 4, 8])
+def test_shim_collectives_under_stress(built, tmp_path, ranks):
+    """The 19-function MPI subset under load, with more ranks than some boxes have cores."""
+    exe = str(tmp_path / "shim_stress")
+    shim = os.path.join(ROOT, "hpc_multigpu_matrixmult_b200", "mpi_shim")
+    lib = os.path.join(ROOT, "hpc_multigpu_matrixmult_b200", "lib")
+    subprocess.run(["gcc", "-O2", "-I", shim, "-o", exe, os.path.join(ROOT, "tests", "csrc", "shim_stress.c"), "-L", lib, "-lphpcmpi",
+                    f"-Wl,-rpath,{lib}"], check=True)
+    res = subprocess.run([os.path.join(ROOT, "bin", "mpirun"), "--oversubscribe", "-n", str(ranks), exe, "1500"], capture_output=True, text=True,
+                         timeout=240)
+    assert res.returncode == 0, res.stdout + res.stderr
+
+
+def test_no_cpu_fallback_without_a_gpu(built):
+    """On a box without a CUDA device the compute entry points abort loudly; nothing computes on the CPU."""
+    import ctypes
+
+    from hpc_multigpu_matrixmult_b200 import capi
+
+    if capi.load().phpc_b200_device_count() > 0:
+        pytest.skip("a GPU is visible here")
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); from hpc_multigpu_matrixmult_b200 import capi; "
+            "a = np.ones((4, 4)); c = np.zeros((4, 4)); capi.phpc_gemm_cuda(a, a, c); print('COMPUTED', c.sum())" % ROOT)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert res.returncode != 0
+    assert "COMPUTED" not in res.stdout
+    assert "no CUDA device visible" in res.stderr and "no CPU fallback" in res.stderr
