@@ -29,7 +29,7 @@ PGRID = {2: "1x2", 8: "2x4"}  # BASELINE.json's orientations (MPI_Dims_create wo
 
 def read_rows(path):
     with open(path) as f:
-        rows = list(csv.DictReader(f))
+        rows = list(csv.DictReader(line for line in f if line.strip() and not line.lstrip().startswith("#")))
     if not rows or any(h not in rows[0] for h in HEADER):
         raise SystemExit(f"{path}: expected header {','.join(HEADER)}")
     return [{h: int(r[h]) for h in HEADER} for r in rows]
