@@ -1,0 +1,70 @@
+"""The Ozaki (tcgen05) arithmetic restated in exact integer arithmetic on the CPU (oracle/ozaki_model.py):
+the digit split is error free, the truncated digit products reach FP64 accuracy with 8 digits, and the
+reference's own input comes out bit-exact.  The GPU test compares the kernel with the model."""
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from oracle import ozaki_model as om
+
+
+def test_digit_split_is_error_free(oracle):
+    a = oracle.fill(6, 40, kind=1, seed=3) * np.ldexp(1.0, np.arange(6) * 17 - 40)[:, None]
+    a[2, :] = 0.0
+    exps = om.exponents(a, 1)
+    digits, rest = om.split_digits(a, exps, 1, 8)
+    assert exps[2] is None and all(np.all(d[2] == 0) for d in digits)
+    for d in digits:
+        assert d.min() >= -127 and d.max() <= 127  # fits a signed int8
+    for i in (0, 1, 3, 5):
+        for j in (0, 7, 39):
+            x = Fraction(float(a[i, j]))
+            recon = sum(Fraction(int(d[i, j]), 1 << (7 * (t + 1))) for t, d in enumerate(digits)) + Fraction(float(rest[i, j])) / (1 << 56)
+            assert recon * Fraction(2) ** exps[i] == x  # exact, not approximately
+        assert abs(a[i]).max() < 2.0 ** exps[i] and abs(a[i]).max() >= 2.0 ** (exps[i] - 1)
+
+
+@pytest.mark.parametrize("m,k,n", [(5, 7, 3), (33, 129, 20), (16, 300, 24)])
+def test_model_reaches_fp64_accuracy_with_8_digits(oracle, m, k, n):
+    a = oracle.fill(m, k, kind=1, seed=5)
+    b = oracle.fill(k, n, kind=1, seed=6)
+    c0 = oracle.fill(m, n, kind=1, seed=7)
+    want = oracle.gemm_block(a, b, c0)
+    got = om.gemm(a, b, c0, S=8)
+    assert oracle.rel_frobenius(got, want) <= 1e-15
+    bound = 4.0 * np.sqrt(k) * 2.0 ** -53 * (np.abs(a) @ np.abs(b)) + 4 * 2.0 ** -53 * np.abs(want)
+    assert np.all(np.abs(got - want) <= bound)
+
+
+def test_model_is_bit_exact_on_the_reference_fill(oracle):
+    for n in (16, 48):
+        a = oracle.fill(n, n, kind=0)
+        assert np.array_equal(om.gemm(a, a, S=8), oracle.index_fill_exact(n))
+        assert np.array_equal(om.gemm(a, a, S=8), oracle.gemm_iterative(a, a))
+
+
+def test_digit_count_sets_the_accuracy(oracle):
+    a = oracle.fill(24, 256, kind=1, seed=1)
+    b = oracle.fill(256, 24, kind=1, seed=2)
+    want = oracle.gemm_block(a, b)
+    errs = {S: oracle.rel_frobenius(om.gemm(a, b, S=S), want) for S in (4, 6, 7, 8)}
+    assert errs[4] > errs[6] > errs[7] > errs[8]
+    assert errs[4] < 1e-6 and errs[6] < 1e-10 and errs[7] < 1e-12 and errs[8] < 1e-15
+
+
+@pytest.mark.gpu
+def test_kernel_matches_the_integer_model(gpu, capi, oracle):
+    """Every operation of the kernel is exact except its two FP64 additions per K chunk, which the
+    model performs in the same order: the results should agree to the last bit (reported), and
+    must agree to 1e-15 (asserted)."""
+    from tests.test_gpu_parity import _device_gemm_from_numpy
+
+    for (m, k, n), slices in (((40, 70, 30), 8), ((33, 129, 65), 8), ((20, 100, 17), 6)):
+        a = oracle.fill(m, k, kind=1, seed=61)
+        b = oracle.fill(k, n, kind=1, seed=62)
+        c0 = oracle.fill(m, n, kind=1, seed=63)
+        got, _ = _device_gemm_from_numpy(capi, gpu, a, b, c0, "ozaki", slices)
+        want = om.gemm(a, b, c0, S=slices)
+        print(f"ozaki kernel vs integer model {m}x{k}x{n} S={slices}: bit-equal={np.array_equal(got, want)}")
+        assert oracle.rel_frobenius(got, want) <= 1e-15
