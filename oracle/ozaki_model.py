@@ -83,3 +83,48 @@ def gemm(a, b, c0=None, S=8):
                     assert abs(v[i, j]) < (1 << 53)
                     c[i, j] = c[i, j] + math.ldexp(float(v[i, j]), ea[i] + eb[j] - DIGIT_BITS * g_hi)
     return c
+
+
+# ----------------------------------------------------------------------------------------------
+# Planned digit scheme — modelled here before it is written in CUDA:
+# first digit signed (floor; 7 bits + sign), further digits UNSIGNED 8 bits (the remainder after a
+# floor is non-negative).  kind::i8 accepts s8 / u8 per operand, so only the split kernels and the
+# instruction descriptors change.  7 digits then carry 7 + 6*8 = 55 bits with 28 digit products, but the
+# truncation error becomes biased (tests/test_ozaki_model.py: ~4e-15 instead of ~1e-15).
+# ----------------------------------------------------------------------------------------------
+def split_digits_mixed(x, exps, axis, S):
+    r = np.array(x, dtype=np.float64, copy=True)
+    scale = np.array([0.0 if e is None else math.ldexp(1.0, -e) for e in exps])
+    r = r * (scale[:, None] if axis == 1 else scale[None, :])
+    digits = []
+    for t in range(S):
+        s = r * (128.0 if t == 0 else 256.0)
+        d = np.floor(s)
+        r = s - d  # in [0, 1)
+        digits.append(d.astype(np.int64))
+    return digits
+
+
+def gemm_mixed(a, b, c0=None, S=7, kc_max=4096):
+    """C = c0 + a @ b with the signed-first / unsigned-rest digits; pair (t,u) weighs 2^-(8(t+u)-2)."""
+    m, k = a.shape
+    n = b.shape[1]
+    c = np.zeros((m, n)) if c0 is None else np.array(c0, dtype=np.float64, copy=True)
+    for k0 in range(0, k, kc_max):
+        ac, bc = a[:, k0:k0 + kc_max], b[k0:k0 + kc_max, :]
+        ea, eb = exponents(ac, 1), exponents(bc, 0)
+        da, db = split_digits_mixed(ac, ea, 1, S), split_digits_mixed(bc, eb, 0, S)
+        assert da[0].min() >= -128 and da[0].max() <= 127 and all(0 <= d.min() and d.max() <= 255 for d in da[1:])
+        total = np.zeros((m, n), dtype=object)  # exact sum of all kept groups, in units of 2^-(8(S+1)-2)
+        for g in range(2, S + 2):
+            acc = np.zeros((m, n), dtype=object)
+            for t in range(max(1, g - S), min(S, g - 1) + 1):
+                acc = acc + (da[t - 1].astype(object) @ db[g - t - 1].astype(object))
+            assert max(abs(int(v)) for v in acc.ravel()) < (1 << 31)  # fits the int32 TMEM accumulator
+            total = total + acc * (1 << (8 * (S + 1 - g)))
+        for i in range(m):
+            for j in range(n):
+                if ea[i] is None or eb[j] is None or total[i, j] == 0:
+                    continue
+                c[i, j] = c[i, j] + math.ldexp(float(total[i, j]), ea[i] + eb[j] - (8 * (S + 1) - 2))  # float(int) rounds once
+    return c

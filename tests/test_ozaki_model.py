@@ -68,3 +68,20 @@ def test_kernel_matches_the_integer_model(gpu, capi, oracle):
         want = om.gemm(a, b, c0, S=slices)
         print(f"ozaki kernel vs integer model {m}x{k}x{n} S={slices}: bit-equal={np.array_equal(got, want)}")
         assert oracle.rel_frobenius(got, want) <= 1e-15
+
+
+def test_planned_mixed_signedness_digits_trade_accuracy_for_fewer_products(oracle):
+    """DESIGN.md section 8 item 1, modelled before it is written in CUDA: signed first digit, unsigned
+    8-bit digits after it.  7 digits = 28 digit products (instead of 36) stay inside the 1e-14 tolerance
+    but are NOT as accurate as 8 signed digits: unsigned digits are never negative, so the dropped
+    low-order groups no longer cancel (measured here: ~4e-15 vs ~6e-16 with 8 mixed digits)."""
+    a = oracle.fill(20, 300, kind=1, seed=11)
+    b = oracle.fill(300, 18, kind=1, seed=12)
+    c0 = oracle.fill(20, 18, kind=1, seed=13)
+    want = oracle.gemm_block(a, b, c0)
+    e7 = oracle.rel_frobenius(om.gemm_mixed(a, b, c0, S=7), want)
+    e8 = oracle.rel_frobenius(om.gemm_mixed(a, b, c0, S=8), want)
+    assert e8 <= 1e-15 < e7 <= 1e-14
+    n = 32
+    ai = oracle.fill(n, n, kind=0)
+    assert np.array_equal(om.gemm_mixed(ai, ai, S=7), oracle.index_fill_exact(n))
