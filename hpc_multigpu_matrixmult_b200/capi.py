@@ -45,6 +45,23 @@ class SummaStep(ctypes.Structure):
     ]
 
 
+class HostOp(ctypes.Structure):
+    """phpc_host_op of include/phpc_summa.h: one operation of the band-pipelined host-sourced run."""
+    _fields_ = [
+        ("kind", ctypes.c_int),
+        ("stream", ctypes.c_int),
+        ("band", ctypes.c_int),
+        ("step", ctypes.c_int),
+        ("row0", ctypes.c_int),
+        ("rows", ctypes.c_int),
+        ("ndeps", ctypes.c_int),
+        ("deps", ctypes.c_int * 3),
+    ]
+
+
+HOP_UPLOAD_C, HOP_UPLOAD_A, HOP_UPLOAD_B, HOP_GEMM, HOP_DOWNLOAD_C = range(5)
+
+
 class SummaStats(ctypes.Structure):
     _fields_ = [
         ("total_ms", ctypes.c_float),
@@ -116,6 +133,8 @@ def load():
 
     L.phpc_summa_schedule.argtypes = [ctypes.c_int] * 6 + [ctypes.POINTER(SummaStep), ctypes.c_int, c_int_p, c_int_p]
     L.phpc_summa_schedule.restype = ctypes.c_int
+    L.phpc_host_plan.argtypes = [ctypes.c_int] * 4 + [ctypes.POINTER(HostOp), ctypes.c_int]
+    L.phpc_host_plan.restype = ctypes.c_int
     L.phpc_summa_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.phpc_summa_create.restype = ctypes.c_void_p
     L.phpc_summa_destroy.argtypes = [ctypes.c_void_p]
@@ -227,6 +246,15 @@ def summa_schedule(N, r, c, pi, pj, kc=0):
     m, n = ctypes.c_int(), ctypes.c_int()
     L.phpc_summa_schedule(N, r, c, pi, pj, kc, steps, count, ctypes.byref(m), ctypes.byref(n))
     return list(steps), m.value, n.value
+
+
+def host_plan(m, nsteps, bands, align=128):
+    """Operation list of the band-pipelined host-sourced run (pure host arithmetic, no GPU)."""
+    L = load()
+    count = L.phpc_host_plan(m, nsteps, bands, align, None, 0)
+    ops = (HostOp * max(count, 1))()
+    L.phpc_host_plan(m, nsteps, bands, align, ops, count)
+    return list(ops)[:count]
 
 
 # ----------------------------------------------------------------------------

@@ -46,6 +46,10 @@ namespace phpc {
 namespace oz {
 
 constexpr int DIGIT_BITS = 7;
+/* EXPERIMENTAL (PHPC_OZAKI_DIGITS=balanced, not validated on hardware in round 1): balanced base-256
+ * digits in [-128,127] of the value rounded to BAL_BITS bits below its row/column scale; 7 digits,
+ * 28 digit products, same accuracy in the integer model (oracle/ozaki_model.py, gemm_balanced). */
+constexpr int BAL_BITS = 54;
 constexpr int MAX_SLICES = 8;
 constexpr int ZERO_EXP = -2147483647 - 1; /* exponent of an all-zero row / column */
 constexpr int NONFINITE_EXP = 2147483647; /* the row / column holds an Inf or NaN: its C elements become NaN */
@@ -151,8 +155,9 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                : "memory");
 }
 
-template <int S_T>
+template <int S_T, bool BAL = false>
 __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) {
+  constexpr int DB = BAL ? 8 : DIGIT_BITS; /* bits between consecutive digit groups */
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
@@ -320,7 +325,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
             int v[32];
             tmem_ld_32x32b_x32(tlane + (uint32_t)(g - g_lo) * BN + c0, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const double w = pow2d(DIGIT_BITS * (g_hi - g));
+            const double w = pow2d(DB * (g_hi - g));
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]);
           }
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
               if (er == NONFINITE_EXP || eb == NONFINITE_EXP)
                 cptr[(long long)rr * p.ldc] = __longlong_as_double(0x7ff8000000000000ll); /* Inf/NaN in the row or column */
               else if (er != ZERO_EXP && x != 0.0)
-                cptr[(long long)rr * p.ldc] = cold[rr] + x * pow2d(er + eb - DIGIT_BITS * g_hi);
+                cptr[(long long)rr * p.ldc] = cold[rr] + x * pow2d(BAL ? er + eb - 2 * BAL_BITS + 8 * (2 * S - g_hi) : er + eb - DIGIT_BITS * g_hi);
             }
           }
           __syncwarp();

@@ -133,5 +133,68 @@ __global__ void split_b_tiled_kernel(const double *__restrict__ B, long long ldb
 }
 
 
+/* ---- EXPERIMENTAL balanced base-256 digits (see BAL_BITS in ozaki_gemm.cuh) ----
+ * q = rint(x * 2^(BAL_BITS - e)) (|q| <= 2^54), written in base 256 with digits in [-128, 127] by carrying
+ * from the least significant end; digit slot 0 is the most significant.  Same tiled store layout. */
+__device__ __forceinline__ void balanced_digits(double x, int e, int S, int8_t *out /* [S], most significant first */) {
+  long long q = (e == ZERO_EXP || e == NONFINITE_EXP) ? 0ll : __double2ll_rn(scalbn(x, BAL_BITS - e));
+  for (int i = S - 1; i >= 0; --i) {
+    const long long d = ((q + 128) & 255) - 128;
+    q = (q - d) >> 8;
+    out[i] = (int8_t)d;
+  }
+}
+
+__global__ void split_a_tiled_balanced_kernel(const double *__restrict__ A, long long lda, int m, int k, int kp, const int *__restrict__ eA,
+                                              int8_t *__restrict__ TA, int S) {
+  const int chunks = kp / 16;
+  const int m_pad = (m + 127) / 128 * 128;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)m_pad * chunks) return;
+  const int chunk = (int)(idx / m_pad), row = (int)(idx % m_pad);
+  const int c0 = chunk * 16;
+  const int e = row < m ? eA[row] : ZERO_EXP;
+  union {
+    int8_t b[MAX_SLICES][16];
+    int4 v[MAX_SLICES];
+  } out;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int c = c0 + j;
+    int8_t dg[MAX_SLICES];
+    balanced_digits((row < m && c < k) ? A[(long long)row * lda + c] : 0.0, e, S, dg);
+    for (int t = 0; t < S; ++t) out.b[t][j] = dg[t];
+  }
+  const int ksteps = kp / 32;
+  const size_t base = (((size_t)(row >> 7) * ksteps + (c0 >> 5)) * S) * 4096 + tile_offset(row & 127, c0 & 31);
+  for (int t = 0; t < S; ++t) *reinterpret_cast<int4 *>(TA + base + (size_t)t * 4096) = out.v[t];
+}
+
+__global__ void split_b_tiled_balanced_kernel(const double *__restrict__ B, long long ldb, int k, int n, int kp, const int *__restrict__ eB,
+                                              int8_t *__restrict__ TB, int S) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_pad = (n + 127) / 128 * 128;
+  if (col >= n_pad) return;
+  const int ks = blockIdx.y;
+  const int k0 = ks * 32;
+  const int e = col < n ? eB[col] : ZERO_EXP;
+  const int ksteps = kp / 32;
+  int8_t *dst0 = TB + (((size_t)(col >> 7) * ksteps + ks) * S) * 4096 + tile_offset(col & 127, 0);
+  for (int half = 0; half < 2; ++half) { /* 16 k bytes = one core-matrix row per half */
+    union {
+      int8_t b[MAX_SLICES][16];
+      int4 v[MAX_SLICES];
+    } out;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int row = k0 + half * 16 + j;
+      int8_t dg[MAX_SLICES];
+      balanced_digits((col < n && row < k) ? B[(long long)row * ldb + col] : 0.0, e, S, dg);
+      for (int t = 0; t < S; ++t) out.b[t][j] = dg[t];
+    }
+    for (int t = 0; t < S; ++t) *reinterpret_cast<int4 *>(dst0 + (size_t)t * 4096 + half * 128) = out.v[t];
+  }
+}
+
 }  // namespace oz
 }  // namespace phpc

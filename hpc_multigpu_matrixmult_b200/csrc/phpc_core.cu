@@ -71,6 +71,7 @@ DeviceCtx *phpc_ctx(int device) {
   CUDA_CHECK(cudaFuncSetAttribute(phpc::dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::GEMM_SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
   load_driver_entry_points();
   ctx->ready = true;
   return ctx;
@@ -244,6 +245,10 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     const char *e = getenv("PHPC_OZAKI_SLICES");
     slices = (e && *e) ? atoi(e) : 8;
   }
+  /* EXPERIMENTAL, opt-in, not validated on hardware in round 1: 7 balanced base-256 digits (28 digit products) */
+  const char *dg = getenv("PHPC_OZAKI_DIGITS");
+  const bool balanced = dg && !strcmp(dg, "balanced");
+  if (balanced) slices = 7;
   PHPC_REQUIRE(slices >= 2 && slices <= MAX_SLICES, "PHPC_OZAKI_SLICES must be in 2..8");
   /* int32 accumulation of a whole group is exact while  K * S * 127^2 < 2^31  (S = 8: K <= 16643) */
   const int kc_max = 8192;
@@ -272,9 +277,14 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     }
     {
       const long long threads = (long long)m_pad * (kp / 16);
-      split_a_tiled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, TA, slices);
       dim3 grid((unsigned)((n_pad + 127) / 128), kp / 32);
-      split_b_tiled_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, TB, slices);
+      if (balanced) {
+        split_a_tiled_balanced_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, TA, slices);
+        split_b_tiled_balanced_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, TB, slices);
+      } else {
+        split_a_tiled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, TA, slices);
+        split_b_tiled_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, TB, slices);
+      }
     }
     Params p;
     p.C = dC;
@@ -293,7 +303,9 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     p.flags = (fl && *fl) ? atoi(fl) : 0;
     int grid = ctx->sm_count;
     if ((long long)grid > tiles) grid = (int)tiles;
-    if (slices == 8)
+    if (balanced)
+      ozaki_gemm_kernel<7, true><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
+    else if (slices == 8)
       ozaki_gemm_kernel<8><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
     else
       ozaki_gemm_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(p);

@@ -94,6 +94,49 @@ extern "C" int phpc_summa_schedule(int N, int r, int c, int pi, int pj, int kc, 
   return count;
 }
 
+/* Band pipeline of the host-sourced run on one GPU (see phpc_host_op in phpc_summa.h).  Issue order:
+ * per band  upload C band, upload its A windows (band 0 also brings every B chunk, interleaved so the
+ * first GEMM can start after one chunk), then the GEMMs of the band over all K chunks in ascending K
+ * (the per-element summation order is the reference's, src/phpc_gemm.cu:33-52), then the download. */
+extern "C" int phpc_host_plan(int m, int nsteps, int bands, int align, phpc_host_op *ops, int max_ops) {
+  if (m <= 0 || nsteps <= 0) return 0;
+  if (bands < 1) bands = 1;
+  if (align < 1) align = 1;
+  int rows_per_band = (m + bands - 1) / bands;
+  rows_per_band = (rows_per_band + align - 1) / align * align;
+  int count = 0;
+  auto emit = [&](int kind, int stream, int band, int step, int row0, int rows, int d0, int d1, int d2) {
+    if (ops && count < max_ops) {
+      phpc_host_op *o = &ops[count];
+      o->kind = kind;
+      o->stream = stream;
+      o->band = band;
+      o->step = step;
+      o->row0 = row0;
+      o->rows = rows;
+      o->ndeps = 0;
+      const int d[3] = {d0, d1, d2};
+      for (int i = 0; i < 3; ++i)
+        if (d[i] >= 0) o->deps[o->ndeps++] = d[i];
+      for (int i = o->ndeps; i < 3; ++i) o->deps[i] = -1;
+    }
+    return count++;
+  };
+  std::vector<int> up_b(nsteps, -1), up_a(nsteps, -1);
+  for (int band = 0, row0 = 0; row0 < m; ++band, row0 += rows_per_band) {
+    const int rows = (m - row0 < rows_per_band) ? m - row0 : rows_per_band;
+    const int up_c = emit(PHPC_HOP_UPLOAD_C, 0, band, -1, row0, rows, -1, -1, -1);
+    for (int q = 0; q < nsteps; ++q) {
+      up_a[q] = emit(PHPC_HOP_UPLOAD_A, 0, band, q, row0, rows, -1, -1, -1);
+      if (band == 0) up_b[q] = emit(PHPC_HOP_UPLOAD_B, 0, -1, q, 0, 0, -1, -1, -1);
+    }
+    int last = -1;
+    for (int q = 0; q < nsteps; ++q) last = emit(PHPC_HOP_GEMM, 1, band, q, row0, rows, q == 0 ? up_c : -1, up_a[q], band == 0 ? up_b[q] : -1);
+    emit(PHPC_HOP_DOWNLOAD_C, 2, band, -1, row0, rows, last, -1, -1);
+  }
+  return count;
+}
+
 /* ------------------------------------------------------------------------- */
 /* NCCL communicators, cached per grid shape                                  */
 /* ------------------------------------------------------------------------- */
@@ -630,9 +673,138 @@ extern "C" void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *user_
   summa_run(s, backend, ctas, user_stream, stats, nullptr, nullptr, nullptr, false);
 }
 
+/* ------------------------------------------------------------------------- */
+/* band-pipelined host-sourced run, one GPU                                   */
+/* ------------------------------------------------------------------------- */
+static int launch_local_gemm(phpc_summa *s, int backend, int ctas, const double *a, long long lda, const double *b, double *c, int rows,
+                             int width, cudaStream_t st) {
+  DeviceCtx *ctx = s->ctx;
+  if (backend == PHPC_BACKEND_CUBLAS) {
+    phpc_launch_cublas(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, st);
+    return 1;
+  }
+  if (backend == PHPC_BACKEND_OZAKI) return phpc_launch_ozaki(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, 0, st);
+  return phpc_launch_dmma(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, ctas, st);
+}
+
+/* Executes the operation list of phpc_host_plan: one CUDA stream per plan stream, one event per
+ * operation that somebody depends on.  The list is verified on the CPU (tests/test_host_plan.py:
+ * every conflicting pair of operations is ordered, every legal execution order gives C + A*B). */
+static void summa_run_host_banded(phpc_summa *s, int backend, int ctas, const double *hA, const double *hB, double *hC, int bands,
+                                  phpc_summa_stats *stats) {
+  PHPC_REQUIRE(s->size == 1, "the band pipeline is the single-rank host path");
+  DeviceCtx *ctx = s->ctx;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  const size_t N = (size_t)s->N;
+  const int nsteps = (int)s->steps.size();
+  const int nops = phpc_host_plan(s->m, nsteps, bands, 128, nullptr, 0);
+  std::vector<phpc_host_op> ops(nops);
+  phpc_host_plan(s->m, nsteps, bands, 128, ops.data(), nops);
+  cudaStream_t streams[3] = {ctx->copy, ctx->compute, ctx->comm}; /* comm is idle on one GPU: it carries the downloads */
+  std::vector<cudaEvent_t> done(nops, nullptr);
+  std::vector<char> needed(nops, 0);
+  for (const phpc_host_op &o : ops)
+    for (int i = 0; i < o.ndeps; ++i) needed[o.deps[i]] = 1;
+  std::vector<cudaEvent_t> g0, g1;
+  int launches = 0;
+  CUDA_CHECK(cudaEventRecord(s->ev_begin, ctx->compute));
+  CUDA_CHECK(cudaStreamWaitEvent(streams[0], s->ev_begin, 0));
+  CUDA_CHECK(cudaStreamWaitEvent(streams[2], s->ev_begin, 0));
+  for (int i = 0; i < nops; ++i) {
+    const phpc_host_op &o = ops[i];
+    cudaStream_t st = streams[o.stream];
+    for (int d = 0; d < o.ndeps; ++d) {
+      PHPC_REQUIRE(o.deps[d] < i && done[o.deps[d]] != nullptr, "host plan dependency does not point at an earlier operation");
+      CUDA_CHECK(cudaStreamWaitEvent(st, done[o.deps[d]], 0));
+    }
+    switch (o.kind) {
+      case PHPC_HOP_UPLOAD_C:
+        CUDA_CHECK(cudaMemcpy2DAsync(s->dC + (size_t)o.row0 * s->ldn, s->ldn * sizeof(double),
+                                     hC + ((size_t)s->pi * s->m + o.row0) * N + (size_t)s->pj * s->n, N * sizeof(double),
+                                     (size_t)s->n * sizeof(double), o.rows, cudaMemcpyHostToDevice, st));
+        break;
+      case PHPC_HOP_UPLOAD_A: {
+        const phpc_summa_step &q = s->steps[o.step];
+        const size_t ld = phpc_pad_ld(q.width);
+        CUDA_CHECK(cudaMemcpy2DAsync(s->dA + q.a_off + (size_t)o.row0 * ld, ld * sizeof(double),
+                                     hA + ((size_t)s->pi * s->m + o.row0) * N + (size_t)q.k0, N * sizeof(double),
+                                     (size_t)q.width * sizeof(double), o.rows, cudaMemcpyHostToDevice, st));
+        break;
+      }
+      case PHPC_HOP_UPLOAD_B: {
+        const phpc_summa_step &q = s->steps[o.step];
+        CUDA_CHECK(cudaMemcpy2DAsync(s->dB + q.b_off, s->ldn * sizeof(double), hB + (size_t)q.k0 * N + (size_t)s->pj * s->n,
+                                     N * sizeof(double), (size_t)s->n * sizeof(double), q.width, cudaMemcpyHostToDevice, st));
+        break;
+      }
+      case PHPC_HOP_GEMM: {
+        const phpc_summa_step &q = s->steps[o.step];
+        const long long ld = phpc_pad_ld(q.width);
+        cudaEvent_t e0, e1;
+        CUDA_CHECK(cudaEventCreate(&e0));
+        CUDA_CHECK(cudaEventCreate(&e1));
+        CUDA_CHECK(cudaEventRecord(e0, st));
+        launches += launch_local_gemm(s, backend, ctas, s->dA + q.a_off + (size_t)o.row0 * ld, ld, s->dB + q.b_off,
+                                      s->dC + (size_t)o.row0 * s->ldn, o.rows, q.width, st);
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        g0.push_back(e0);
+        g1.push_back(e1);
+        break;
+      }
+      case PHPC_HOP_DOWNLOAD_C:
+        CUDA_CHECK(cudaMemcpy2DAsync(hC + ((size_t)s->pi * s->m + o.row0) * N + (size_t)s->pj * s->n, N * sizeof(double),
+                                     s->dC + (size_t)o.row0 * s->ldn, s->ldn * sizeof(double), (size_t)s->n * sizeof(double), o.rows,
+                                     cudaMemcpyDeviceToHost, st));
+        break;
+      default:
+        PHPC_REQUIRE(false, "unknown host plan operation");
+    }
+    if (needed[i]) {
+      CUDA_CHECK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventRecord(done[i], st));
+    }
+  }
+  CUDA_CHECK(cudaEventRecord(s->ev_end, ctx->compute));
+  for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaStreamSynchronize(streams[i]));
+  if (stats) {
+    float total = 0.f, gemm = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&total, s->ev_begin, s->ev_end));
+    for (size_t i = 0; i < g0.size(); ++i) {
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, g0[i], g1[i]));
+      gemm += ms;
+    }
+    stats->total_ms = total;
+    stats->gemm_ms = gemm;
+    stats->exposed_ms = total - gemm;
+    stats->steps = nsteps;
+    stats->launches = launches;
+    stats->broadcasts = 0;
+    stats->bytes_received = 0;
+  }
+  for (cudaEvent_t e : done)
+    if (e) CUDA_CHECK(cudaEventDestroy(e));
+  for (cudaEvent_t e : g0) CUDA_CHECK(cudaEventDestroy(e));
+  for (cudaEvent_t e : g1) CUDA_CHECK(cudaEventDestroy(e));
+}
+
+/* Row bands of the single-GPU host-sourced run: PHPC_HOST_BANDS, else 8 once the block is big enough
+ * for the C transfers to matter (>= 8192 rows), else 1 (= the chunk-pipelined loop above). */
+static int host_bands(const phpc_summa *s) {
+  if (s->size != 1) return 1;
+  const int e = env_int("PHPC_HOST_BANDS", 0);
+  if (e > 0) return e;
+  return s->m >= 8192 ? 8 : 1;
+}
+
 extern "C" void phpc_summa_run_host(phpc_summa *s, int backend, int ctas, const double *A, const double *B, double *C, int gather,
                                     phpc_summa_stats *stats) {
   phpc_summa_stats local;
+  const int bands = host_bands(s);
+  if (bands > 1 && A && B && C) {
+    summa_run_host_banded(s, backend, ctas, A, B, C, bands, stats ? stats : &local);
+    return;
+  }
   summa_run(s, backend, ctas, nullptr, stats ? stats : &local, A, B, C, true);
   phpc_summa_download_c(s, C, gather);
   if (s->size > 1 && s->transport == 1) MPI_Barrier(s->grid_comm); /* peers are done pulling before the next upload */

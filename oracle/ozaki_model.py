@@ -128,3 +128,43 @@ def gemm_mixed(a, b, c0=None, S=7, kc_max=4096):
                     continue
                 c[i, j] = c[i, j] + math.ldexp(float(total[i, j]), ea[i] + eb[j] - (8 * (S + 1) - 2))  # float(int) rounds once
     return c
+
+
+# Balanced base-256 digits (the candidate that keeps the cancellation): the scaled value is rounded to a
+# 54-bit integer Q (|x| * 2^-e * 2^54), Q is written in base 256 with digits in [-128, 127] (carry from
+# the least significant end), all digits signed 8-bit.  7 digits, 28 digit products, weights 256^-(t+u).
+def split_digits_balanced(x, exps, axis, S=7, bits=54):
+    r = np.array(x, dtype=np.float64, copy=True)
+    scale = np.array([0.0 if e is None else math.ldexp(1.0, bits - e) for e in exps])
+    q = np.rint(r * (scale[:, None] if axis == 1 else scale[None, :])).astype(np.int64)  # |q| <= 2^54, exact scaling + one rounding
+    digits = []
+    for _ in range(S):
+        d = ((q + 128) % 256) - 128
+        q = (q - d) // 256
+        digits.append(d)
+    assert np.all(q == 0)
+    return digits[::-1]  # most significant first: x ~ 2^(e-bits) * sum_t d_t 256^(S-1-t)
+
+
+def gemm_balanced(a, b, c0=None, S=7, kc_max=8192, bits=54):
+    m, k = a.shape
+    n = b.shape[1]
+    c = np.zeros((m, n)) if c0 is None else np.array(c0, dtype=np.float64, copy=True)
+    for k0 in range(0, k, kc_max):
+        ac, bc = a[:, k0:k0 + kc_max], b[k0:k0 + kc_max, :]
+        ea, eb = exponents(ac, 1), exponents(bc, 0)
+        da, db = split_digits_balanced(ac, ea, 1, S, bits), split_digits_balanced(bc, eb, 0, S, bits)
+        total = np.zeros((m, n), dtype=object)
+        for g in range(2, S + 2):  # keep pairs with t+u <= S+1 (1-based, most significant first)
+            acc = np.zeros((m, n), dtype=object)
+            for t in range(max(1, g - S), min(S, g - 1) + 1):
+                acc = acc + (da[t - 1].astype(object) @ db[g - t - 1].astype(object))
+            assert max(abs(int(v)) for v in acc.ravel()) < (1 << 31)
+            total = total + acc * (1 << (8 * (S + 1 - g)))
+        # pair (t,u) weighs 256^(2S-t-u); `total` is in units of 256^(S-1) (the dropped groups are below it)
+        for i in range(m):
+            for j in range(n):
+                if ea[i] is None or eb[j] is None or total[i, j] == 0:
+                    continue
+                c[i, j] = c[i, j] + math.ldexp(float(total[i, j]), ea[i] + eb[j] - 2 * bits + 8 * (S - 1))
+    return c

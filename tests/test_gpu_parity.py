@@ -402,3 +402,45 @@ def test_ozaki_nonfinite_inputs_poison_their_row_and_column(gpu, capi, oracle):
     a2[3, :] = 0.0
     b2[:, 5] = 0.0
     assert oracle.rel_frobenius(c[mask], oracle.gemm_block(a2, b2)[mask]) <= 1e-14
+
+
+@pytest.mark.parametrize("mode", ["ozaki", "dmma"])
+def test_host_bands_bit_identical_to_chunk_pipeline(gpu, capi, oracle, mode):
+    """The band pipeline of the single-GPU host path (PHPC_HOST_BANDS; default 8 bands once the block has
+    >= 8192 rows) only reorders independent work: per element the K chunks are still added in ascending
+    order, so the result must equal the chunk-pipelined loop bit for bit, and the reference's own
+    input must still come out exact.  Its operation list is proven race free in tests/test_host_plan.py."""
+    import os
+
+    lib = gpu
+    n = 1024
+    comm = capi.cart_create((1, 1))
+    A = oracle.fill(n, n, kind=1, seed=oracle.SEED_A)
+    B = oracle.fill(n, n, kind=1, seed=oracle.SEED_B)
+    C0 = oracle.fill(n, n, kind=1, seed=77)
+    Ai = oracle.fill(n, n, kind=0)
+    saved = {k: os.environ.get(k) for k in ("PHPC_GEMM", "PHPC_KC", "PHPC_HOST_BANDS")}
+    out = {}
+    try:
+        os.environ["PHPC_GEMM"] = mode
+        os.environ["PHPC_KC"] = "256"  # 4 K chunks
+        for bands in (1, 3):  # 3 bands of 384, 384, 256 rows
+            os.environ["PHPC_HOST_BANDS"] = str(bands)
+            lib.phpc_summa_release_cache()
+            C = C0.copy()
+            capi.phpc_gemm_summa_cuda(comm, A, B, C)
+            capi.phpc_gemm_summa_cuda(comm, A, B, C)  # second pass on the same C, as reference main.c does
+            Ci = np.zeros((n, n))
+            capi.phpc_gemm_summa_cuda(comm, Ai, Ai.copy(), Ci)
+            out[bands] = (C, Ci)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        lib.phpc_summa_release_cache()
+    assert np.array_equal(out[1][0], out[3][0])
+    assert np.array_equal(out[3][1], oracle.index_fill_exact(n))
+    want = C0 + 2.0 * oracle.gemm_block(A, B)
+    assert oracle.rel_frobenius(out[3][0], want) <= 1e-14
