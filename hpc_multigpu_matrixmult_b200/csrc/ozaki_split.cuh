@@ -133,11 +133,23 @@ __global__ void split_b_tiled_kernel(const double *__restrict__ B, long long ldb
 }
 
 
-/* ---- EXPERIMENTAL balanced base-256 digits (see BAL_BITS in ozaki_gemm.cuh) ----
- * q = rint(x * 2^(BAL_BITS - e)) (|q| <= 2^54), written in base 256 with digits in [-128, 127] by carrying
- * from the least significant end; digit slot 0 is the most significant.  Same tiled store layout. */
-__device__ __forceinline__ void balanced_digits(double x, int e, int S, int8_t *out /* [S], most significant first */) {
+/* ======================================================================================================
+ * EXPERIMENTAL split kernels (opt-in through PHPC_OZAKI_DIGITS / PHPC_OZAKI_KERNEL, see phpc_launch_ozaki):
+ *   - balanced base-256 digits (BAL_BITS in ozaki_gemm.cuh): 7 digits, 28 digit products instead of 36;
+ *   - the B store in "half-major" order for the 2-CTA kernel (ozaki_gemm2.cuh): each CTA of a pair reads
+ *     the 64 B^T rows (output columns) of its half of every digit tile as one contiguous range.
+ * Their bodies are __host__ __device__ so the very same lines run on the CPU in tests/test_ozaki_split_host.py
+ * (tests/csrc/oz_host_probe.cu) against the integer model in oracle/ozaki_model.py.
+ * ====================================================================================================== */
+
+/* q = rint(x * 2^(BAL_BITS - e)) (|q| <= 2^54), written in base 256 with digits in [-128, 127] by carrying
+ * from the least significant end; digit slot 0 is the most significant. */
+__host__ __device__ __forceinline__ void balanced_digits(double x, int e, int S, int8_t *out /* [S], most significant first */) {
+#ifdef __CUDA_ARCH__
   long long q = (e == ZERO_EXP || e == NONFINITE_EXP) ? 0ll : __double2ll_rn(scalbn(x, BAL_BITS - e));
+#else
+  long long q = (e == ZERO_EXP || e == NONFINITE_EXP) ? 0ll : llrint(scalbn(x, BAL_BITS - e));
+#endif
   for (int i = S - 1; i >= 0; --i) {
     const long long d = ((q + 128) & 255) - 128;
     q = (q - d) >> 8;
@@ -145,55 +157,91 @@ __device__ __forceinline__ void balanced_digits(double x, int e, int S, int8_t *
   }
 }
 
-__global__ void split_a_tiled_balanced_kernel(const double *__restrict__ A, long long lda, int m, int k, int kp, const int *__restrict__ eA,
-                                              int8_t *__restrict__ TA, int S) {
+/* digits of one value, most significant first: BAL = false is the truncating 7-bit scheme of the kernels above */
+template <bool BAL, int S>
+__host__ __device__ __forceinline__ void digits_of(double x, int e, int8_t *out) {
+  if (BAL) {
+    balanced_digits(x, e, S, out);
+    return;
+  }
+  double r = (e == ZERO_EXP || e == NONFINITE_EXP) ? 0.0 : scalbn(x, -e);
+#pragma unroll
+  for (int t = 0; t < S; ++t) {
+    const double s = r * 128.0;
+    const int d = (int)s;
+    r = s - (double)d;
+    out[t] = (int8_t)d;
+  }
+}
+
+/* byte offset of (row, global k byte, digit t) in a tiled digit store.  halves = 1: store[row tile][k step][digit][4 KiB]
+ * (the layout of the kernels above); halves = 2: store[row tile][k step][half][digit][2 KiB], rows 0..63 / 64..127 */
+__host__ __device__ __forceinline__ size_t store_offset(int row, int kbyte, int t, int S, int ksteps, int halves) {
+  const int tile = row >> 7, r = row & 127, ks = kbyte >> 5, kb = kbyte & 31;
+  const int rows_per_half = 128 / halves, h = r / rows_per_half, rh = r % rows_per_half;
+  return ((((size_t)tile * ksteps + ks) * halves + h) * S + t) * ((size_t)rows_per_half * 32) + tile_offset(rh, kb);
+}
+
+/* A: work item = 16 consecutive k of one padded row (m_pad = rows of the store: a multiple of 128, of 256 for the 2-CTA kernel) */
+template <bool BAL, int S>
+__host__ __device__ __forceinline__ void split_a_body(long long idx, const double *__restrict__ A, long long lda, int m, int m_pad, int k,
+                                                      int kp, const int *__restrict__ eA, int8_t *__restrict__ TA) {
   const int chunks = kp / 16;
-  const int m_pad = (m + 127) / 128 * 128;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)m_pad * chunks) return;
   const int chunk = (int)(idx / m_pad), row = (int)(idx % m_pad);
   const int c0 = chunk * 16;
   const int e = row < m ? eA[row] : ZERO_EXP;
   union {
-    int8_t b[MAX_SLICES][16];
-    int4 v[MAX_SLICES];
+    int8_t b[S][16];
+    int4 v[S];
   } out;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const int c = c0 + j;
-    int8_t dg[MAX_SLICES];
-    balanced_digits((row < m && c < k) ? A[(long long)row * lda + c] : 0.0, e, S, dg);
+    int8_t dg[S];
+    digits_of<BAL, S>((row < m && c < k) ? A[(long long)row * lda + c] : 0.0, e, dg);
+#pragma unroll
     for (int t = 0; t < S; ++t) out.b[t][j] = dg[t];
   }
-  const int ksteps = kp / 32;
-  const size_t base = (((size_t)(row >> 7) * ksteps + (c0 >> 5)) * S) * 4096 + tile_offset(row & 127, c0 & 31);
-  for (int t = 0; t < S; ++t) *reinterpret_cast<int4 *>(TA + base + (size_t)t * 4096) = out.v[t];
+#pragma unroll
+  for (int t = 0; t < S; ++t) *reinterpret_cast<int4 *>(TA + store_offset(row, c0, t, S, kp / 32, 1)) = out.v[t];
 }
 
-__global__ void split_b_tiled_balanced_kernel(const double *__restrict__ B, long long ldb, int k, int n, int kp, const int *__restrict__ eB,
-                                              int8_t *__restrict__ TB, int S) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n_pad = (n + 127) / 128 * 128;
+/* B (transposed): work item = the 32 k of one k step of one padded column */
+template <bool BAL, int S>
+__host__ __device__ __forceinline__ void split_b_body(int col, int ks, const double *__restrict__ B, long long ldb, int k, int n, int n_pad,
+                                                      int kp, const int *__restrict__ eB, int8_t *__restrict__ TB, int halves) {
   if (col >= n_pad) return;
-  const int ks = blockIdx.y;
   const int k0 = ks * 32;
   const int e = col < n ? eB[col] : ZERO_EXP;
-  const int ksteps = kp / 32;
-  int8_t *dst0 = TB + (((size_t)(col >> 7) * ksteps + ks) * S) * 4096 + tile_offset(col & 127, 0);
-  for (int half = 0; half < 2; ++half) { /* 16 k bytes = one core-matrix row per half */
+  for (int half16 = 0; half16 < 2; ++half16) { /* 16 k bytes = one core-matrix row */
     union {
-      int8_t b[MAX_SLICES][16];
-      int4 v[MAX_SLICES];
+      int8_t b[S][16];
+      int4 v[S];
     } out;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int row = k0 + half * 16 + j;
-      int8_t dg[MAX_SLICES];
-      balanced_digits((col < n && row < k) ? B[(long long)row * ldb + col] : 0.0, e, S, dg);
+      const int row = k0 + half16 * 16 + j;
+      int8_t dg[S];
+      digits_of<BAL, S>((col < n && row < k) ? B[(long long)row * ldb + col] : 0.0, e, dg);
+#pragma unroll
       for (int t = 0; t < S; ++t) out.b[t][j] = dg[t];
     }
-    for (int t = 0; t < S; ++t) *reinterpret_cast<int4 *>(dst0 + (size_t)t * 4096 + half * 128) = out.v[t];
+#pragma unroll
+    for (int t = 0; t < S; ++t) *reinterpret_cast<int4 *>(TB + store_offset(col, k0 + half16 * 16, t, S, kp / 32, halves)) = out.v[t];
   }
+}
+
+template <bool BAL, int S>
+__global__ void split_a_tiled_v2_kernel(const double *__restrict__ A, long long lda, int m, int m_pad, int k, int kp,
+                                        const int *__restrict__ eA, int8_t *__restrict__ TA) {
+  split_a_body<BAL, S>((long long)blockIdx.x * blockDim.x + threadIdx.x, A, lda, m, m_pad, k, kp, eA, TA);
+}
+
+template <bool BAL, int S>
+__global__ void split_b_tiled_v2_kernel(const double *__restrict__ B, long long ldb, int k, int n, int n_pad, int kp,
+                                        const int *__restrict__ eB, int8_t *__restrict__ TB, int halves) {
+  split_b_body<BAL, S>(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y, B, ldb, k, n, n_pad, kp, eB, TB, halves);
 }
 
 }  // namespace oz

@@ -10,6 +10,7 @@
 #include "../../include/phpc_gemm.cuh"
 #include "dmma_gemm.cuh"
 #include "ozaki_gemm.cuh"
+#include "ozaki_gemm2.cuh"
 #include "ozaki_split.cuh"
 #include "phpc_internal.h"
 
@@ -71,7 +72,10 @@ DeviceCtx *phpc_ctx(int device) {
   CUDA_CHECK(cudaFuncSetAttribute(phpc::dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::GEMM_SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
+  /* experimental variants (opt-in, see phpc_launch_ozaki) */
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_2cta_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM2_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_2cta_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM2_BYTES));
   load_driver_entry_points();
   ctx->ready = true;
   return ctx;
@@ -245,10 +249,14 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     const char *e = getenv("PHPC_OZAKI_SLICES");
     slices = (e && *e) ? atoi(e) : 8;
   }
-  /* EXPERIMENTAL, opt-in, not validated on hardware in round 1: 7 balanced base-256 digits (28 digit products) */
-  const char *dg = getenv("PHPC_OZAKI_DIGITS");
+  /* EXPERIMENTAL, opt-in, not validated on hardware in round 1 (tools/ozaki_variants.py validates them):
+   *   PHPC_OZAKI_DIGITS=balanced  7 balanced base-256 digits: 28 digit products instead of 36
+   *   PHPC_OZAKI_KERNEL=2cta      CTA pairs, cta_group::2 MMAs with M = 256 (ozaki_gemm2.cuh) */
+  const char *dg = getenv("PHPC_OZAKI_DIGITS"), *kn = getenv("PHPC_OZAKI_KERNEL");
   const bool balanced = dg && !strcmp(dg, "balanced");
+  const bool two_cta = kn && !strcmp(kn, "2cta");
   if (balanced) slices = 7;
+  PHPC_REQUIRE(!two_cta || slices == (balanced ? 7 : 8), "the 2-CTA kernel is built for 8 truncated or 7 balanced digits");
   PHPC_REQUIRE(slices >= 2 && slices <= MAX_SLICES, "PHPC_OZAKI_SLICES must be in 2..8");
   /* int32 accumulation of a whole group is exact while  K * S * 127^2 < 2^31  (S = 8: K <= 16643) */
   const int kc_max = 8192;
@@ -256,7 +264,8 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
   const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
   const long long tiles = (long long)tiles_m * tiles_n;
   PHPC_REQUIRE(tiles < (1ll << 30), "too many output tiles");
-  const size_t m_pad = (size_t)tiles_m * BM, n_pad = (size_t)tiles_n * BN;
+  const int tiles_m_store = two_cta ? (tiles_m + 1) / 2 * 2 : tiles_m; /* a CTA pair works on two row tiles: pad with a zero tile */
+  const size_t m_pad = (size_t)tiles_m_store * BM, n_pad = (size_t)tiles_n * BN;
   const char *pf = getenv("PHPC_OZ_PF"), *fl = getenv("PHPC_OZ_FLAGS"); /* diagnostics, see profiles/ozaki_experiments_r01.md */
   for (int k0 = 0; k0 < k; k0 += kc_max) {
     const int kc = (k - k0 < kc_max) ? k - k0 : kc_max;
@@ -278,9 +287,16 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     {
       const long long threads = (long long)m_pad * (kp / 16);
       dim3 grid((unsigned)((n_pad + 127) / 128), kp / 32);
-      if (balanced) {
-        split_a_tiled_balanced_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, TA, slices);
-        split_b_tiled_balanced_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, TB, slices);
+      if (balanced || two_cta) {
+        const unsigned a_blocks = (unsigned)((threads + 255) / 256);
+        const int halves = two_cta ? 2 : 1;
+        if (balanced) {
+          split_a_tiled_v2_kernel<true, 7><<<a_blocks, 256, 0, stream>>>(a, lda, m, (int)m_pad, kc, kp, eA, TA);
+          split_b_tiled_v2_kernel<true, 7><<<grid, 128, 0, stream>>>(b, ldb, kc, n, (int)n_pad, kp, eB, TB, halves);
+        } else {
+          split_a_tiled_v2_kernel<false, 8><<<a_blocks, 256, 0, stream>>>(a, lda, m, (int)m_pad, kc, kp, eA, TA);
+          split_b_tiled_v2_kernel<false, 8><<<grid, 128, 0, stream>>>(b, ldb, kc, n, (int)n_pad, kp, eB, TB, halves);
+        }
       } else {
         split_a_tiled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, TA, slices);
         split_b_tiled_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, TB, slices);
@@ -301,14 +317,26 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     p.TB = TB;
     p.prefetch = (pf && *pf) ? atoi(pf) : 0;
     p.flags = (fl && *fl) ? atoi(fl) : 0;
-    int grid = ctx->sm_count;
-    if ((long long)grid > tiles) grid = (int)tiles;
-    if (balanced)
-      ozaki_gemm_kernel<7, true><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
-    else if (slices == 8)
-      ozaki_gemm_kernel<8><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
-    else
-      ozaki_gemm_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
+    if (two_cta) {
+      p.tiles_m = tiles_m_store;
+      const long long pair_tiles = (long long)(tiles_m_store / 2) * tiles_n;
+      long long clusters = ctx->sm_count / 2;
+      if (clusters > pair_tiles) clusters = pair_tiles;
+      const int grid2 = (int)(2 * clusters); /* __cluster_dims__(2,1,1): CTAs 2c and 2c+1 form pair c */
+      if (balanced)
+        ozaki_gemm_2cta_kernel<7, true><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p);
+      else
+        ozaki_gemm_2cta_kernel<8, false><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p);
+    } else {
+      int grid = ctx->sm_count;
+      if ((long long)grid > tiles) grid = (int)tiles;
+      if (balanced)
+        ozaki_gemm_kernel<7, true><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
+      else if (slices == 8)
+        ozaki_gemm_kernel<8><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
+      else
+        ozaki_gemm_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
+    }
     CUDA_CHECK(cudaGetLastError());
     launches += 6;
   }

@@ -85,3 +85,25 @@ def test_planned_mixed_signedness_digits_trade_accuracy_for_fewer_products(oracl
     n = 32
     ai = oracle.fill(n, n, kind=0)
     assert np.array_equal(om.gemm_mixed(ai, ai, S=7), oracle.index_fill_exact(n))
+
+
+def test_balanced_base256_digits_keep_the_accuracy_with_28_products(oracle):
+    """The experimental digit scheme of PHPC_OZAKI_DIGITS=balanced (csrc/ozaki_split.cuh, balanced_digits): the value
+    rounded to 54 bits below its row/column scale, written in base 256 with digits in [-128, 127].  7 digits = 28
+    digit products instead of 36, and because balanced digits keep their sign the dropped low-order groups still
+    cancel: the model is as accurate as 8 truncated 7-bit digits (the mixed-signedness variant above is not)."""
+    for (m, k, n) in ((20, 300, 18), (9, 1000, 12)):
+        a = oracle.fill(m, k, kind=1, seed=11)
+        b = oracle.fill(k, n, kind=1, seed=12)
+        c0 = oracle.fill(m, n, kind=1, seed=13)
+        want = oracle.gemm_block(a, b, c0)
+        e_bal = oracle.rel_frobenius(om.gemm_balanced(a, b, c0, S=7), want)
+        e_8 = oracle.rel_frobenius(om.gemm(a, b, c0, S=8), want)
+        assert e_bal <= 2e-15 and e_bal <= 1.5 * e_8
+    a = oracle.fill(12, 200, kind=1, seed=14) * np.ldexp(1.0, np.arange(12) * 40 - 250)[:, None]  # rows 2^-250 .. 2^190
+    b = oracle.fill(200, 10, kind=1, seed=15)
+    assert oracle.rel_frobenius(om.gemm_balanced(a, b, S=7), oracle.gemm_block(a, b)) <= 2e-15
+    ai = oracle.fill(32, 32, kind=0)
+    assert np.array_equal(om.gemm_balanced(ai, ai, S=7), oracle.index_fill_exact(32))
+    d = om.split_digits_balanced(a, om.exponents(a, 1), 1, 7)
+    assert all(x.min() >= -128 and x.max() <= 127 for x in d)
