@@ -172,6 +172,14 @@ def int8_peak():
         return 2.0 * 1590.0, "fallback: 2 x bf16 fallback peak (profiles/umma_rate_r01.jsonl missing)"
 
 
+def measured_peaks():
+    """MEASURED_PEAKS.json (driver-written on this pool: HBM copy GB/s, cuBLAS bf16 burst / sustained TFLOP/s), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        return None
+
+
 def host_matrices(capi, N, dims, coords, pin=True):
     """FULL N x N host A, B, C as the reference API wants them; only the windows this rank
     owns are filled and page-locked (the rest of the address range is never touched)."""
@@ -384,8 +392,12 @@ def product_arm(args):
     s.fill(capi.FILL_SEEDED)
     stream = torch.cuda.current_stream()
     sptr = ctypes.c_void_p(stream.cuda_stream)
-    slices = int(os.environ.get("PHPC_OZAKI_SLICES", "8"))
+    balanced = os.environ.get("PHPC_OZAKI_DIGITS") == "balanced"  # experimental variants of phpc_launch_ozaki (opt-in)
+    two_cta = os.environ.get("PHPC_OZAKI_KERNEL") == "2cta"
+    slices = 7 if balanced else int(os.environ.get("PHPC_OZAKI_SLICES", "8"))
     pairs = slices * (slices + 1) // 2
+    oz_kernel = (f"phpc::oz::ozaki_gemm_2cta_kernel<{slices}> (tcgen05.mma.cta_group::2 kind::i8, M=256 per CTA pair" if two_cta
+                 else f"phpc::oz::ozaki_gemm_kernel<{slices}> (tcgen05.mma kind::i8") + ", int32 accumulators in TMEM, cp.async.bulk ring)"
     fp64_pk, fp64_src = fp64_peak()
     int8_pk, int8_src = int8_peak()
 
@@ -417,11 +429,23 @@ def product_arm(args):
         gemm_tflops = 2.0 * m_blk * n_blk * k_per_gemm / (gemm_ms * 1e-3) / 1e12
         if backend == capi.BACKEND_OZAKI:
             roof = {"bound": "tensor", "achieved": gemm_tflops * pairs, "peak": int8_pk, "unit": "TOP/s", "frac": gemm_tflops * pairs / int8_pk,
-                    "traffic": None, "kernel": "phpc::oz3::ozaki_gemm_kernel_v3<8> (tcgen05.mma kind::i8, int32 accumulators in TMEM, cp.async.bulk ring)",
+                    "traffic": None, "kernel": oz_kernel,
                     "ops_per_launch": 2.0 * m_blk * n_blk * k_per_gemm * pairs, "kernel_ms": gemm_ms, "fp64_equivalent_tflops": gemm_tflops,
                     "fp64_equivalent_vs_fp64_peak": gemm_tflops / fp64_pk, "peak_source": int8_src,
-                    "note": f"{pairs} int8 MMAs per FP64 MMA ({slices} digits); kernel_ms spans the whole local GEMM (exponent + split kernels "
-                            "included, < 3 % at this size)"}
+                    "note": f"{pairs} int8 MMAs per FP64 MMA ({slices} {'balanced base-256' if balanced else 'truncated 7-bit'} digits); kernel_ms spans the whole local GEMM (exponent + split kernels "
+                            "included, < 3 % at this size)",
+                    "traffic_note": "no ncu --set full capture of this launch shape yet; the N=8192 launch of the same kernel family read 11.5 GB "
+                                    "and wrote 1.1 GB of DRAM (algorithmic: 1.07 GB of digits + 2 passes x 1.07 GB of C) = 8.5 % of HBM peak, "
+                                    "profiles/ncu_ozaki_gemm_n8192_r01_v3.txt"}
+            mp = measured_peaks()
+            if mp and mp.get("bf16_tflops") and mp.get("bf16_tflops_sustained"):
+                # the step is seconds long and power capped: scale the burst int8 peak by the driver's sustained/burst bf16 ratio,
+                # and show the fraction against 2 x the driver's own bf16 numbers (int8 = 2 x bf16 nominally) beside it
+                ratio = mp["bf16_tflops_sustained"] / mp["bf16_tflops"]
+                roof["frac_of_sustained_estimate"] = gemm_tflops * pairs / (int8_pk * ratio)
+                roof["sustained_estimate_source"] = (f"burst int8 peak x MEASURED_PEAKS.json bf16 sustained/burst ({ratio:.3f}); a sustained int8 "
+                                                     "microbenchmark with random operands is tools/umma_rate.cu UMMA_SUSTAIN=1 (not yet run)")
+                roof["frac_of_2x_measured_bf16_sustained"] = gemm_tflops * pairs / (2.0 * mp["bf16_tflops_sustained"])
         else:
             roof = {"bound": "tensor", "achieved": gemm_tflops, "peak": fp64_pk, "unit": UNIT, "frac": gemm_tflops / fp64_pk,
                     "traffic": DMMA_N32768_DRAM_BYTES if (world == 1 and N == 32768 and st.steps == 1) else None,
@@ -472,8 +496,9 @@ def product_arm(args):
             "data": "synthetic",
             "config": {"workload": f"SUMMA C+=A*B, N={N}, FP64 in/out, splitmix64-seeded uniform(-1,1) A/B generated in HBM, owned blocks device-resident",
                        "local_gemm": names[primary],
-                       "arithmetic": ("FP64 rebuilt exactly from 8 signed 7-bit digits per operand: s8 x s8 -> s32 on tcgen05, FP64 recombination "
-                                      "(rel. Frobenius difference to native FP64 1.5e-15)") if primary == capi.BACKEND_OZAKI else "native FP64 DMMA",
+                       "arithmetic": (f"FP64 rebuilt exactly from {slices} signed {'8-bit balanced' if balanced else '7-bit'} digits per operand: "
+                                      "s8 x s8 -> s32 on tcgen05, FP64 recombination (rel. Frobenius difference to native FP64 1.5e-15)")
+                       if primary == capi.BACKEND_OZAKI else "native FP64 DMMA",
                        "N": N, "process_grid": f"{dims[0]}x{dims[1]}", "k_chunk": kc_used, "summa_steps": steps_per_summa,
                        "cache": "inputs_larger_than_l2 (operands are GiBs; L2 is 126 MB)", "exposed_broadcast_frac": exposed_frac,
                        "nvlink_bytes_received_rank0_per_step": bytes_rx},

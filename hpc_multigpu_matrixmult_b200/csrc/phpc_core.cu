@@ -72,10 +72,6 @@ DeviceCtx *phpc_ctx(int device) {
   CUDA_CHECK(cudaFuncSetAttribute(phpc::dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::GEMM_SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
-  /* experimental variants (opt-in, see phpc_launch_ozaki) */
-  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_2cta_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM2_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_2cta_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM2_BYTES));
   load_driver_entry_points();
   ctx->ready = true;
   return ctx;
@@ -317,6 +313,12 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     p.TB = TB;
     p.prefetch = (pf && *pf) ? atoi(pf) : 0;
     p.flags = (fl && *fl) ? atoi(fl) : 0;
+    if (balanced || two_cta) { /* experimental kernels opt in to their shared memory here, not at context creation:
+                                * nothing about them may affect the default path */
+      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    }
     if (two_cta) {
       p.tiles_m = tiles_m_store;
       const long long pair_tiles = (long long)(tiles_m_store / 2) * tiles_n;

@@ -13,7 +13,7 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-struct Cfg { int kind; int M; int N; int accs; int reps; int swz; };   /* kind 0 = i8, 1 = f8f6f4 (e4m3), 2 = f16 (bf16) */
+struct Cfg { int kind; int M; int N; int accs; int reps; int swz; int rnd; };  /* rnd: pseudo-random operand bytes instead of zeros */   /* kind 0 = i8, 1 = f8f6f4 (e4m3), 2 = f16 (bf16) */
 
 __device__ __forceinline__ uint64_t desc_noswz(uint32_t saddr) {
   uint64_t d = 0; d |= (uint64_t)((saddr & 0x3FFFF) >> 4); d |= (uint64_t)(128 >> 4) << 16; d |= (uint64_t)(256 >> 4) << 32; d |= (uint64_t)1 << 46; return d;
@@ -26,7 +26,18 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(Cfg c, long long *cyc
   extern __shared__ unsigned char smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar = base + 96 * 1024, slot = bar + 16;
-  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 4 * i), "r"(0));
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) {
+    /* zeros do not toggle the datapath (a zero-operand run is not a sustained peak): rnd fills with a hash.  For the
+     * float kinds the hash is masked so that no byte pattern is an Inf/NaN (exponent bits never all ones). */
+    uint32_t v = 0;
+    if (c.rnd) {
+      v = (uint32_t)(i + 1) * 2654435761u + blockIdx.x * 40503u;
+      v ^= v >> 15; v *= 2246822519u; v ^= v >> 13;
+      if (c.kind == 1) v &= 0xB7B7B7B7u;       /* e4m3: clear one exponent bit per byte */
+      else if (c.kind == 2) v &= 0xBF7FBF7Fu;  /* bf16: clear the top exponent bit of each half word */
+    }
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 4 * i), "r"(v));
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
@@ -98,16 +109,22 @@ int main() {
     {1,128,128,4,4000,0},{1,128,256,2,4000,0},{1,128,256,2,4000,1},
     {2,128,128,4,4000,0},{2,128,256,2,4000,0},{2,128,256,2,4000,1},
   };
-  if (getenv("UMMA_SUSTAIN")) { /* seconds-long run of the best int8 shape: the power-capped (sustained) int8 peak */
-    Cfg c = {0, 128, 256, 2, 40000000, 0};
-    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0)); umma_rate_kernel<<<sms, 128, smem>>>(c, d); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
-    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
-    printf("{\"kind\": \"i8\", \"M\": 128, \"N\": 256, \"K\": 32, \"sustained_seconds\": %.2f, \"chip_tops_sustained\": %.1f}\n", ms * 1e-3,
-           2.0 * 128 * 256 * 32 * (double)c.reps * sms / (ms * 1e-3) / 1e12);
+  if (getenv("UMMA_SUSTAIN")) { /* seconds-long runs of the best int8 shape: the power-capped (sustained) int8 peak.
+                                 * zero operands first (round 1: 4.4 POP/s, the datapath does not toggle), then random bytes */
+    for (int rnd = 0; rnd < 2; ++rnd) {
+      Cfg c = {0, 128, 256, 2, 40000000, 0, rnd};
+      cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      CK(cudaEventRecord(e0)); umma_rate_kernel<<<sms, 128, smem>>>(c, d); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+      float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+      printf("{\"kind\": \"i8\", \"M\": 128, \"N\": 256, \"K\": 32, \"operands\": \"%s\", \"sustained_seconds\": %.2f, \"chip_tops_sustained\": %.1f}\n",
+             rnd ? "random" : "zero", ms * 1e-3, 2.0 * 128 * 256 * 32 * (double)c.reps * sms / (ms * 1e-3) / 1e12);
+      fflush(stdout);
+    }
     return 0;
   }
+  const int rnd_all = getenv("UMMA_RANDOM") ? 1 : 0; /* burst table with random operand bytes */
   for (auto &c : cfgs) {
+    c.rnd = rnd_all;
     for (int one_sm = 0; one_sm < 2; ++one_sm) {
       const int grid = one_sm ? 1 : sms;
       cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -118,8 +135,8 @@ int main() {
       double avg = 0; long long mx = 0; for (int i = 0; i < grid; ++i) { avg += h[i]; if (h[i] > mx) mx = h[i]; } avg /= grid;
       const int K = c.kind == 2 ? 16 : 32;
       const double macs = (double)c.M * c.N * K;
-      printf("{\"kind\": \"%s\", \"M\": %d, \"N\": %d, \"K\": %d, \"accumulators\": %d, \"layout\": \"%s\", \"sms\": %d, \"cycles_per_mma\": %.1f, "
-             "\"mac_per_clk_per_sm\": %.0f, \"chip_tops_at_event_time\": %.1f}\n", kinds[c.kind], c.M, c.N, K, c.accs, c.swz ? "sw128" : "noswz", grid,
+      printf("{\"kind\": \"%s\", \"M\": %d, \"N\": %d, \"K\": %d, \"accumulators\": %d, \"layout\": \"%s\", \"operands\": \"%s\", \"sms\": %d, \"cycles_per_mma\": %.1f, "
+             "\"mac_per_clk_per_sm\": %.0f, \"chip_tops_at_event_time\": %.1f}\n", kinds[c.kind], c.M, c.N, K, c.accs, c.swz ? "sw128" : "noswz", c.rnd ? "random" : "zero", grid,
              avg / c.reps, macs / (avg / c.reps), 2.0 * macs * c.reps * grid / (ms * 1e-3) / 1e12);
       fflush(stdout);
     }
