@@ -283,7 +283,7 @@ def e2e_measure(args, capi, L, comm, dims, rank, world, barrier, max_over_ranks)
     for ptr, _ in regs:
         L.phpc_host_unregister(ptr)
     L.phpc_summa_release_cache()
-    bands = os.environ.get("PHPC_HOST_BANDS", "8 (default for blocks of >= 8192 rows)") if world == 1 else "n/a"
+    bands = os.environ.get("PHPC_HOST_BANDS", "4 (default for blocks of >= 8192 rows)") if world == 1 else "n/a"
     return {"value": flops / secs / 1e12 if ok is not False else None, "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * N * N,
             "d2h_bytes_per_step": 8 * N * N, "ms_per_step": secs * 1e3, "steps": e2e_steps, "verified": ok, "host_row_bands": bands,
             "api": "phpc_gemm_summa_cuda(grid_comm, A, B, C, N, ...) on page-locked full N x N host matrices; owned blocks H2D, C block "

@@ -788,13 +788,17 @@ static void summa_run_host_banded(phpc_summa *s, int backend, int ctas, const do
   for (cudaEvent_t e : g1) CUDA_CHECK(cudaEventDestroy(e));
 }
 
-/* Row bands of the single-GPU host-sourced run: PHPC_HOST_BANDS, else 8 once the block is big enough
- * for the C transfers to matter (>= 8192 rows), else 1 (= the chunk-pipelined loop above). */
+/* Row bands of the single-GPU host-sourced run: PHPC_HOST_BANDS, else 4 once the block is big enough
+ * for the C transfers to matter (>= 8192 rows), else 1 (= the chunk-pipelined loop above).  Why 4 at
+ * N = 32768 (PCIe ~55 GB/s, GEMM ~1 s): band 0 must bring all of B (8.6 GB) + its A and C bands
+ * (2 x 2.1 GB) = 0.23 s of H2D under 0.26 s of compute, so it is not upload bound (with 8 bands it is);
+ * every band repeats the split of the B chunks (Ozaki) = +0.4 % per band; the exposed tail is the last
+ * band's download (0.04 s). */
 static int host_bands(const phpc_summa *s) {
   if (s->size != 1) return 1;
   const int e = env_int("PHPC_HOST_BANDS", 0);
   if (e > 0) return e;
-  return s->m >= 8192 ? 8 : 1;
+  return s->m >= 8192 ? 4 : 1;
 }
 
 extern "C" void phpc_summa_run_host(phpc_summa *s, int backend, int ctas, const double *A, const double *B, double *C, int gather,

@@ -1,0 +1,29 @@
+#!/usr/bin/env bash
+# gpu_session.sh — the first GPU call of a round, in one command (1 GPU):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/gpu_session.sh'
+# Stages (each bounded by its own timeout, outputs under gpurun_out/; a failing stage does not stop the next):
+#   tests     python -m pytest tests -m gpu
+#   variants  tools/ozaki_variants.py: parity + timing of the experimental Ozaki kernels (balanced digits, 2-CTA)
+#   peaks     bin/umma_rate: burst table with random operands, sustained int8 peak (zero and random operands)
+#   ncu       launch list of a short bench run + one --set full capture of the Ozaki GEMM kernel at the bench launch shape
+#   bench     python bench.py (N=32768, value + band-pipelined e2e + roofline + cpu_baseline)
+# Choose stages with STAGES="tests variants ..." (default: all).
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+STAGES="${STAGES:-tests variants peaks ncu bench}"
+run() { local name=$1 limit=$2; shift 2; echo "=== $name"; timeout "$limit" "$@"; echo "=== $name exit $?"; }
+for s in $STAGES; do
+  case $s in
+    tests)    run tests 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log ;;
+    variants) run variants 900 python tools/ozaki_variants.py --out gpurun_out/ozaki_variants.jsonl ;;
+    peaks)    run umma_random 120 env UMMA_RANDOM=1 bin/umma_rate > gpurun_out/umma_rate_random.jsonl 2> gpurun_out/umma_rate.err
+              run umma_sustain 120 env UMMA_SUSTAIN=1 bin/umma_rate > gpurun_out/umma_rate_sustained.jsonl 2>> gpurun_out/umma_rate.err
+              tail -2 gpurun_out/umma_rate_sustained.jsonl ;;
+    ncu)      run ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+                  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-secondary > gpurun_out/ncu_bench.log 2>&1
+              run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:ozaki_gemm -s 1 -c 1 -o gpurun_out/prof_ozaki_bench_shape -f \
+                  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-secondary > gpurun_out/ncu_full.log 2>&1 ;;
+    bench)    run bench 1500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench.err; tail -c 1500 gpurun_out/bench_n1.json ;;
+  esac
+done

@@ -406,7 +406,7 @@ def test_ozaki_nonfinite_inputs_poison_their_row_and_column(gpu, capi, oracle):
 
 @pytest.mark.parametrize("mode", ["ozaki", "dmma"])
 def test_host_bands_bit_identical_to_chunk_pipeline(gpu, capi, oracle, mode):
-    """The band pipeline of the single-GPU host path (PHPC_HOST_BANDS; default 8 bands once the block has
+    """The band pipeline of the single-GPU host path (PHPC_HOST_BANDS; default 4 bands once the block has
     >= 8192 rows) only reorders independent work: per element the K chunks are still added in ascending
     order, so the result must equal the chunk-pipelined loop bit for bit, and the reference's own
     input must still come out exact.  Its operation list is proven race free in tests/test_host_plan.py."""
