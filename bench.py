@@ -70,6 +70,41 @@ def run_reference_cpu(n, opt="O0"):
     return 2.0 * n ** 3 / secs / 1e12, secs, kind
 
 
+def run_reference_cuda_build(n=8192, tile=32, gw=64, gh=64, timeout=300):
+    """The reference's OWN CUDA+MPI program on this box: oracle/_ref/ref_main.out = /root/reference/src/{main.c, phpc_summa.c,
+    phpc_gemm.cu, utils.c} compiled unchanged against the MPI shim (oracle/Makefile), one rank, one GPU.  It times its CUDA pass
+    (host-memory SUMMA + H2D + gemm_kernel + D2H, src/main.c:93-95) and its cuBLASXt pass (:105-107) itself and writes the
+    reference's CSV record (src/utils.c:26-27); this returns those numbers as TFLOP/s.  Launch grid gw x gh CTAs of tile x tile
+    threads (the reference's own sweeps use 1 x 1 .. 8 x 8 CTAs; 64 x 64 is the generous setting)."""
+    import tempfile
+
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_main.out")
+    mpirun = os.path.join(ROOT, "bin", "mpirun")
+    if not (os.path.exists(exe) and os.path.exists(mpirun)):
+        return {"unavailable": "oracle/_ref/ref_main.out or bin/mpirun not built"}
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "csv"))
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+        try:
+            p = subprocess.run([mpirun, "-n", "1", exe, str(n), str(tile), str(gw), str(gh), "bench"], cwd=tmp, env=env, capture_output=True,
+                               text=True, timeout=timeout)
+        except subprocess.TimeoutExpired:
+            return {"unavailable": f"timed out after {timeout} s at N={n}"}
+        files = os.listdir(os.path.join(tmp, "csv"))
+        if p.returncode != 0 or not files:
+            return {"unavailable": f"exit {p.returncode}: {p.stderr.strip()[-200:]}"}
+        rec = open(os.path.join(tmp, "csv", files[0])).read().strip().split(",")
+    cuda_s, kernel_s, cublas_s = float(rec[6]), float(rec[7]), float(rec[8])
+    fl = 2.0 * n ** 3 / 1e12
+    return {"N": n, "launch": f"{gw}x{gh} CTAs of {tile}x{tile} threads", "ranks": 1, "gpus": 1,
+            "cuda_pass_tflops": fl / cuda_s if cuda_s > 0 else None, "cuda_pass_s": cuda_s,
+            "gemm_kernel_tflops": fl / kernel_s if kernel_s > 0 else None, "gemm_kernel_s": kernel_s,
+            "cublasxt_pass_tflops": fl / cublas_s if cublas_s > 0 else None, "cublasxt_pass_s": cublas_s,
+            "what": "the reference's unmodified main.c + phpc_summa.c + phpc_gemm.cu (oracle/_ref/ref_main.out), timed by itself: wall time of "
+                    "its CUDA pass (includes CUDA context creation, host pinning, H2D/D2H per call) and of its cuBLASXt pass, "
+                    "event time of its kernel"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -489,6 +524,13 @@ def product_arm(args):
             cpu["value_O3"] = v3
             cpu["sample"] += f"; same source with -O3: {s3:.3f} s"
 
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_refcuda:
+        try:
+            ref_cuda = run_reference_cuda_build()
+        except Exception as e:  # a reported baseline must never cost the bench line
+            ref_cuda = {"unavailable": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -507,6 +549,7 @@ def product_arm(args):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": prim["roofline"],
             "cpu_baseline": cpu,
+            "reference_cuda_build": ref_cuda,
             "local_gemm": names[primary],
             names[secondary]: other,
         }
@@ -533,6 +576,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-child", action="store_true", help="internal: run only the single-GPU e2e leg and print it")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-refcuda", action="store_true", help="skip the run of the reference's own CUDA build (oracle/_ref/ref_main.out)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the second local-GEMM kernel")
     args = ap.parse_args()
     if args.e2e_child:

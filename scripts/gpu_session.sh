@@ -21,9 +21,9 @@ for s in $STAGES; do
               run umma_sustain 120 env UMMA_SUSTAIN=1 bin/umma_rate > gpurun_out/umma_rate_sustained.jsonl 2>> gpurun_out/umma_rate.err
               tail -2 gpurun_out/umma_rate_sustained.jsonl ;;
     ncu)      run ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-                  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-secondary > gpurun_out/ncu_bench.log 2>&1
+                  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-refcuda --no-secondary > gpurun_out/ncu_bench.log 2>&1
               run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:ozaki_gemm -s 1 -c 1 -o gpurun_out/prof_ozaki_bench_shape -f \
-                  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-secondary > gpurun_out/ncu_full.log 2>&1 ;;
+                  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-refcuda --no-secondary > gpurun_out/ncu_full.log 2>&1 ;;
     bench)    run bench 1500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench.err; tail -c 1500 gpurun_out/bench_n1.json ;;
   esac
 done
