@@ -81,6 +81,8 @@ struct Params {
   const int8_t *TB; /* [tiles_n][ksteps][S][4096] */
   int prefetch;     /* k steps of L2 prefetch ahead of the shared-memory ring (0 = off) */
   int flags;        /* diagnostics: 1 = epilogue skips the C read-modify-write, 2 = no operand loads (MMA rate only) */
+  unsigned int *progress; /* bring-up aid of the experimental 2-CTA kernel (PHPC_OZ_PROGRESS=1): host-mapped words, 8 per CTA,
+                           * where every warp role records how far it got, readable from the host WHILE a kernel hangs */
 };
 
 /* instruction descriptor: s8 x s8 -> s32, A and B K-major */

@@ -85,6 +85,15 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
                : "memory");
 }
 
+/* progress word of one warp role: (stage marker << 28) | (units done & 0xfffffff); slot 0 producer, 1 MMA issuer / relay,
+ * 2..5 epilogue warps, 6 set-up / tear-down.  Markers: 1 waiting for a barrier, 2 past it, 3 role finished. */
+__device__ __forceinline__ void progress_mark(const Params &p, int slot, uint32_t marker, uint32_t count) {
+  if (p.progress) {
+    volatile unsigned int *w = p.progress + (size_t)blockIdx.x * 8 + slot;
+    *w = (marker << 28) | (count & 0x0fffffffu);
+  }
+}
+
 /* Params as in ozaki_gemm.cuh with: tiles_m = number of 128-row tiles rounded up to EVEN (TA holds zero digits
  * for the padding tile), TB in half-major order. */
 template <int S_T, bool BAL>
@@ -126,16 +135,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) progress_mark(p, 6, 1, 0);
   cluster_sync_all(); /* the peer's barriers exist before anything arrives on them remotely */
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  if (threadIdx.x == 0) progress_mark(p, 6, 2, tmem_base);
 
   if (warp == 0) {
     /* ===== producer (both CTAs): own A rows + own half of the B digit tiles ===== */
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, loads = 0;
       const size_t a_step = (size_t)S * SLOT_BYTES, b_step = (size_t)2 * S * B_HALF_BYTES;
       for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
         int tm2, tn;
@@ -150,7 +161,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
           const uint32_t a_bytes = (uint32_t)d_hi * SLOT_BYTES, b_bytes = (uint32_t)d_hi * B_HALF_BYTES;
           for (int ks = 0; ks < p.ksteps; ks += sub) {
             const int nsub = min(sub, p.ksteps - ks);
+            progress_mark(p, 0, 1, loads);
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            progress_mark(p, 0, 2, loads++);
             const uint32_t full = full0 + 8 * stage;
             mbar_expect_tx(full, (a_bytes + b_bytes) * nsub);
             const uint32_t sa = smem_base + stage * STAGE2_BYTES;
@@ -166,12 +179,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
           }
         }
       }
+      progress_mark(p, 0, 3, loads);
     }
   } else if (warp == 1 && !leader) {
     /* ===== peer CTA: forward "my operands of this stage have landed" to the leader ===== */
     if (lane == 0) {
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, fwd = 0;
       const uint32_t leader_pfull0 = map_to_cta(pfull0, 0);
       for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
 #pragma unroll 1
@@ -180,8 +194,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
           const int d_hi = min(S, g_hi - 1);
           const int sub = (2 * d_hi <= MAX_S) ? 2 : 1;
           for (int ks = 0; ks < p.ksteps; ks += sub) {
+            progress_mark(p, 1, 1, fwd);
             mbar_wait(full0 + 8 * stage, phase);
             mbar_arrive_cluster(leader_pfull0 + 8 * stage);
+            progress_mark(p, 1, 2, fwd++);
             if (++stage == STAGES2) {
               stage = 0;
               phase ^= 1;
@@ -189,13 +205,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
           }
         }
       }
+      progress_mark(p, 1, 3, fwd);
     }
   } else if (warp == 1) {
     /* ===== leader CTA: MMA issuer for the pair (warp-uniform loops, one elected lane issues) ===== */
     const uint32_t idesc = idesc_i8(2 * BM, BN);
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t unit = 0;
+    uint32_t unit = 0, steps = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += nclusters) {
 #pragma unroll
       for (int ps = 0; ps < NPASS; ++ps, ++unit) {
@@ -203,13 +220,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
         const int g_lo = max(2, g_hi - GROUPS_PER_PASS + 1);
         const int d_hi = min(S, g_hi - 1);
         const int sub = (2 * d_hi <= MAX_S) ? 2 : 1;
+        if (lane == 0) progress_mark(p, 1, 4, unit);
         mbar_wait_cluster(tempty, (unit & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
         for (int ks = 0; ks < p.ksteps; ks += sub) {
           const int nsub = min(sub, p.ksteps - ks);
+          if (lane == 0) progress_mark(p, 1, 1, steps);
           mbar_wait(full0 + 8 * stage, phase);
+          if (lane == 0) progress_mark(p, 1, 5, steps);
           mbar_wait_cluster(pfull0 + 8 * stage, phase);
+          if (lane == 0) progress_mark(p, 1, 2, steps++);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_base + stage * STAGE2_BYTES;
           const uint32_t sb = sa + MAX_S * SLOT_BYTES;
@@ -242,6 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
         __syncwarp();
       }
     }
+    if (lane == 0) progress_mark(p, 1, 3, steps);
   } else {
     /* ===== epilogue (both CTAs, own 128 rows): as ozaki_gemm.cuh, tempty lives in the leader ===== */
     const int quarter = warp & 3;
@@ -259,7 +281,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
       for (int ps = 0; ps < NPASS; ++ps, ++unit) {
         const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
         const int g_lo = max(2, g_hi - GROUPS_PER_PASS + 1);
+        if (lane == 0) progress_mark(p, warp, 1, unit);
         mbar_wait(tfull, unit & 1);
+        if (lane == 0) progress_mark(p, warp, 2, unit);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
@@ -306,12 +330,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
         if (lane == 0) mbar_arrive_cluster(leader_tempty);
       }
     }
+    if (lane == 0) progress_mark(p, warp, 3, unit);
   }
 
   /* both CTAs are done with each other's tensor memory and barriers before either one leaves */
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) progress_mark(p, 6, 4, 0);
   cluster_sync_all();
+  if (threadIdx.x == 0) progress_mark(p, 6, 3, 0);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");

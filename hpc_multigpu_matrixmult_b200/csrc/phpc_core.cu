@@ -236,6 +236,36 @@ int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const doub
 /* ------------------------------------------------------------------------- */
 /* Ozaki (int8 tcgen05) launcher                                              */
 /* ------------------------------------------------------------------------- */
+/* Bring-up aid of the experimental 2-CTA kernel (PHPC_OZ_PROGRESS=1): 8 host-mapped words per CTA in which every
+ * warp role records how far it got (ozaki_gemm2.cuh, progress_mark).  The host can read them while a kernel hangs:
+ * tools/ozaki_variants.py launches, polls phpc_compute_stream_idle() and dumps phpc_oz_progress_read() on a timeout. */
+static unsigned int *g_oz_progress = nullptr;
+static int g_oz_progress_words = 0;
+static unsigned int *oz_progress_buffer(int ctas) {
+  const char *e = getenv("PHPC_OZ_PROGRESS");
+  if (!(e && *e && atoi(e) != 0)) return nullptr;
+  if (!g_oz_progress) {
+    g_oz_progress_words = 8 * ctas;
+    CUDA_CHECK(cudaHostAlloc((void **)&g_oz_progress, g_oz_progress_words * sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable));
+  }
+  memset(g_oz_progress, 0, g_oz_progress_words * sizeof(unsigned int));
+  unsigned int *dev = nullptr;
+  CUDA_CHECK(cudaHostGetDevicePointer((void **)&dev, g_oz_progress, 0));
+  return dev;
+}
+extern "C" int phpc_oz_progress_read(unsigned int *out, int max_words) {
+  if (!g_oz_progress) return 0;
+  const int n = g_oz_progress_words < max_words ? g_oz_progress_words : max_words;
+  for (int i = 0; i < n; ++i) out[i] = ((volatile unsigned int *)g_oz_progress)[i];
+  return n;
+}
+extern "C" int phpc_compute_stream_idle(void) {
+  DeviceCtx *ctx = phpc_cur_ctx();
+  const cudaError_t e = cudaStreamQuery(ctx->compute);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) return 0;
+  phpc_die("cudaStreamQuery(compute)", cudaGetErrorString(e), __FILE__, __LINE__);
+}
 int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                       int k, int n, int slices, cudaStream_t stream) {
   using namespace phpc::oz;
@@ -313,6 +343,7 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     p.TB = TB;
     p.prefetch = (pf && *pf) ? atoi(pf) : 0;
     p.flags = (fl && *fl) ? atoi(fl) : 0;
+    p.progress = two_cta ? oz_progress_buffer(ctx->sm_count) : nullptr;
     if (balanced || two_cta) { /* experimental kernels opt in to their shared memory here, not at context creation:
                                 * nothing about them may affect the default path */
       CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -91,6 +91,13 @@ void phpc_fill_device(double *d, long long ld, long long rows, long long cols, l
 void phpc_fill_host(double *h, long long ld, long long rows, long long cols, long long row0, long long col0, long long N, int kind,
                     unsigned long long seed);
 
+/* ---- bring-up diagnostics of the experimental 2-CTA kernel (PHPC_OZAKI_KERNEL=2cta, PHPC_OZ_PROGRESS=1) ---- */
+/* 1 when everything enqueued on the library's compute stream has finished, 0 while work is pending (never blocks). */
+int phpc_compute_stream_idle(void);
+/* Copies the host-mapped progress words (8 per CTA: producer, MMA issuer / relay, 4 epilogue warps, set-up) of the last
+ * 2-CTA launch; works WHILE that kernel runs or hangs.  Returns the number of words written (0 when not enabled). */
+int phpc_oz_progress_read(unsigned int *out, int max_words);
+
 #ifdef __cplusplus
 }
 #endif

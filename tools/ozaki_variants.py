@@ -26,11 +26,37 @@ sys.path.insert(0, ROOT)
 VARIANTS = {
     "default": {},
     "balanced": {"PHPC_OZAKI_DIGITS": "balanced"},
-    "2cta": {"PHPC_OZAKI_KERNEL": "2cta"},
-    "2cta+balanced": {"PHPC_OZAKI_KERNEL": "2cta", "PHPC_OZAKI_DIGITS": "balanced"},
+    "2cta": {"PHPC_OZAKI_KERNEL": "2cta", "PHPC_OZ_PROGRESS": "1"},
+    "2cta+balanced": {"PHPC_OZAKI_KERNEL": "2cta", "PHPC_OZAKI_DIGITS": "balanced", "PHPC_OZ_PROGRESS": "1"},
 }
 SHAPES = [(128, 128, 128), (256, 128, 128), (128, 64, 256), (100, 77, 50), (384, 1000, 300), (640, 333, 257), (1024, 1024, 1024),
           (300, 9000, 200), (2048, 2048, 1536)]
+
+
+ROLES = ["producer", "mma/relay", "epi0", "epi1", "epi2", "epi3", "setup", "-"]
+MARKS = {0: "not started", 1: "waiting", 2: "passed", 3: "finished", 4: "waiting(tempty/cluster)", 5: "own full ok, waiting peer_full"}
+
+
+def wait_or_report_hang(L, shape, seconds=20.0):
+    """Poll the compute stream; if the kernel is still running after `seconds`, print where every warp role of the first
+    CTA pairs stands (progress words of the 2-CTA kernel, PHPC_OZ_PROGRESS=1) and leave: the parent records a hang."""
+    import ctypes
+    import time
+
+    t0 = time.time()
+    while time.time() - t0 < seconds:
+        if L.phpc_compute_stream_idle():
+            return
+        time.sleep(0.01)
+    words = (ctypes.c_uint * 4096)()
+    L.phpc_oz_progress_read.argtypes = [ctypes.POINTER(ctypes.c_uint), ctypes.c_int]
+    n = L.phpc_oz_progress_read(words, 4096)
+    ctas = []
+    for c in range(min(n // 8, 6)):
+        ctas.append({ROLES[r]: f"{MARKS.get(words[c * 8 + r] >> 28, words[c * 8 + r] >> 28)}@{words[c * 8 + r] & 0x0fffffff}" for r in range(7)})
+    stuck = sum(1 for c in range(n // 8) if (words[c * 8 + 6] >> 28) != 3)
+    print(json.dumps({"hang": list(shape), "seconds": seconds, "ctas_not_finished": stuck, "ctas_total": n // 8, "first_ctas": ctas}), flush=True)
+    os._exit(3)
 
 
 def worker(times):
@@ -60,7 +86,9 @@ def worker(times):
         for d in (dC1, dC2):
             L.phpc_copy2d_to_device(d, ldb, c0.ctypes.data_as(dp), ldb, m, ldb)
         L.phpc_gemm_device(dA, lda, dB, ldb, dC1, ldb, m, k, n, 0, None)
-        L.phpc_gemm_device_ozaki(dA, lda, dB, ldb, dC2, ldb, m, k, n, 0, None)
+        L.phpc_device_synchronize()
+        L.phpc_gemm_device_ozaki(dA, lda, dB, ldb, dC2, ldb, m, k, n, 0, None)  # enqueues only
+        wait_or_report_hang(L, (m, k, n))
         L.phpc_device_synchronize()
         c1 = capi.device_window(dC1, ldb, 0, 0, m, n)
         c2 = capi.device_window(dC2, ldb, 0, 0, m, n)
@@ -123,9 +151,10 @@ def main():
             for l in lines:
                 out.write(json.dumps({"variant": name, **json.loads(l)}) + "\n")
             checks = [json.loads(l) for l in lines if '"check"' in l]
+            hangs = [json.loads(l) for l in lines if '"hang"' in l]
             summary = {"variant": name, "exit": rc, "checks": len(checks), "failed": sum(1 for c in checks if not c["ok"]),
                        "tflops": {json.loads(l)["time_n"]: round(json.loads(l)["fp64_equivalent_tflops"], 1) for l in lines if '"time_n"' in l},
-                       "stderr_tail": stderr.strip()[-400:] if rc != 0 else ""}
+                       "hang": hangs[0] if hangs else None, "stderr_tail": stderr.strip()[-400:] if rc != 0 else ""}
             out.write(json.dumps({"summary": summary}) + "\n")
             out.flush()
             print(json.dumps(summary), flush=True)
