@@ -284,8 +284,17 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
   if (balanced) slices = 7;
   PHPC_REQUIRE(!two_cta || slices == (balanced ? 7 : 8), "the 2-CTA kernel is built for 8 truncated or 7 balanced digits");
   PHPC_REQUIRE(slices >= 2 && slices <= MAX_SLICES, "PHPC_OZAKI_SLICES must be in 2..8");
-  /* int32 accumulation of a whole group is exact while  K * S * 127^2 < 2^31  (S = 8: K <= 16643) */
-  const int kc_max = 8192;
+  /* int32 accumulation of a whole group is exact while  K * S * 127^2 < 2^31  (S = 8: K <= 16643; 7 balanced digits,
+   * |digit| <= 128: K <= 18724).  Default K chunk 8192; PHPC_OZ_KC (multiple of 128, <= 16384) trades digit-store
+   * size for half as many epilogues (the C read-modify-write is ~5 % of a chunk at 8192). */
+  int kc_max = 8192;
+  {
+    const char *e = getenv("PHPC_OZ_KC");
+    if (e && *e) {
+      kc_max = atoi(e);
+      PHPC_REQUIRE(kc_max >= 128 && kc_max <= 16384 && kc_max % 128 == 0, "PHPC_OZ_KC must be a multiple of 128 in 128..16384");
+    }
+  }
   int launches = 0;
   const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
   const long long tiles = (long long)tiles_m * tiles_n;
