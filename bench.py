@@ -207,6 +207,23 @@ def int8_peak():
         return 2.0 * 1590.0, "fallback: 2 x bf16 fallback peak (profiles/umma_rate_r01.jsonl missing)"
 
 
+def int8_sustained_peak():
+    """Sustained (seconds-long, power-capped) int8 tensor peak on RANDOM operands, if it has been measured on this pool:
+    UMMA_SUSTAIN=1 bin/umma_rate -> profiles/umma_rate_sustained*_r*.jsonl (scripts/gpu_session.sh, stage `peaks`)."""
+    import glob
+
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "umma_rate_sustained*.jsonl"))):
+        try:
+            for l in open(path):
+                d = json.loads(l)
+                if d.get("operands") == "random" and "chip_tops_sustained" in d:
+                    best = (d["chip_tops_sustained"], os.path.relpath(path, ROOT))
+        except (OSError, ValueError):
+            continue
+    return best
+
+
 def measured_peaks():
     """MEASURED_PEAKS.json (driver-written on this pool: HBM copy GB/s, cuBLAS bf16 burst / sustained TFLOP/s), or None."""
     try:
@@ -472,6 +489,11 @@ def product_arm(args):
                     "traffic_note": "no ncu --set full capture of this launch shape yet; the N=8192 launch of the same kernel family read 11.5 GB "
                                     "and wrote 1.1 GB of DRAM (algorithmic: 1.07 GB of digits + 2 passes x 1.07 GB of C) = 8.5 % of HBM peak, "
                                     "profiles/ncu_ozaki_gemm_n8192_r01_v3.txt"}
+            sus = int8_sustained_peak()
+            if sus:
+                roof["peak_sustained"] = sus[0]
+                roof["frac_of_sustained"] = gemm_tflops * pairs / sus[0]
+                roof["peak_sustained_source"] = f"tcgen05.mma kind::i8 128x256x32 on random operand bytes, seconds-long run under the power cap ({sus[1]})"
             mp = measured_peaks()
             if mp and mp.get("bf16_tflops") and mp.get("bf16_tflops_sustained"):
                 # the step is seconds long and power capped: scale the burst int8 peak by the driver's sustained/burst bf16 ratio,
