@@ -1,0 +1,182 @@
+"""bench.py's control flow and JSON contract exercised on the CPU with the CUDA library and torch.cuda replaced by
+stand-ins (the numbers are meaningless; the point is that every key the driver reads is produced, that the e2e leg
+verifies its result and refuses to report a wrong one, and that no code path of bench.py raises).  The real
+measurement needs a B200: `python bench.py`."""
+import argparse
+import ctypes
+import io
+import json
+import sys
+import types
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+
+import bench
+
+
+class _Stats:
+    total_ms, gemm_ms, exposed_ms, steps, launches, broadcasts, bytes_received = 10.0, 9.5, 0.5, 1, 6, 0, 0
+
+
+class _FakeSumma:
+    def __init__(self, comm, n, kc=0):
+        self.block = (n, n)
+
+    def fill(self, kind):
+        pass
+
+    def run(self, backend, ctas, stream, stats=True):
+        return _Stats() if stats else None
+
+    def destroy(self):
+        pass
+
+
+class _FakeLib:
+    def __getattr__(self, name):  # every C entry point: accept anything, return 1 (device count etc.)
+        return lambda *a, **k: 1
+
+
+def _fake_capi(wrong_result=False):
+    m = types.ModuleType("capi")
+    m.BACKEND_DMMA, m.BACKEND_CUBLAS, m.BACKEND_OZAKI = 0, 1, 2
+    m.FILL_INDEX, m.FILL_SEEDED, m.SEED_A, m.SEED_B = 0, 1, 1234, 5678
+    m.c_double_p = ctypes.POINTER(ctypes.c_double)
+    lib = _FakeLib()
+
+    def fill_host(ptr, ld, rows, cols, row0, col0, N, kind, seed):
+        a = np.ctypeslib.as_array(ptr, shape=(rows * ld,))
+        rng = np.random.default_rng(seed + row0 * 7 + col0)
+        for r in range(rows):
+            a[r * ld:r * ld + cols] = rng.uniform(-1, 1, cols)
+        return 0
+
+    lib.phpc_fill_host = fill_host
+    m.load = lambda: lib
+    m.mpi_init = lambda *a: None
+    m.cart_create = lambda dims: 0
+    m.Summa = _FakeSumma
+
+    def summa_cuda(comm, A, B, C):
+        C += A @ B
+        if wrong_result:
+            C[0, 0] += 1.0
+        return 0.001
+
+    m.phpc_gemm_summa_cuda = summa_cuda
+    return m
+
+
+class _FakeEvent:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self, stream=None):
+        pass
+
+    def elapsed_time(self, other):
+        return 30.0
+
+
+@pytest.fixture
+def fake_cuda(monkeypatch):
+    import torch
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: types.SimpleNamespace(cuda_stream=0))
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("LOCAL_RANK", raising=False)
+
+
+def _args(**kw):
+    d = dict(gpus=1, steps=2, warmup=1, impl="b200", n=64, kc=0, e2e_steps=1, no_e2e=False, no_cpu=True, no_refcuda=True, no_secondary=False,
+             e2e_child=False)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def test_product_arm_prints_the_contract_line(monkeypatch, fake_cuda):
+    import hpc_multigpu_matrixmult_b200 as pkg
+
+    monkeypatch.setattr(pkg, "capi", _fake_capi(), raising=False)
+    monkeypatch.setitem(sys.modules, "hpc_multigpu_matrixmult_b200.capi", pkg.capi)
+    # the e2e leg normally runs in a child process; here it runs in-process against the stand-in library
+    monkeypatch.setattr(bench, "e2e_in_child",
+                        lambda args: bench.e2e_measure(args, pkg.capi, pkg.capi.load(), 0, (1, 1), 0, 1, lambda: None, lambda x: x))
+    out = io.StringIO()
+    with redirect_stdout(out):
+        bench.product_arm(_args())
+    lines = [l for l in out.getvalue().splitlines() if l.startswith("{")]
+    assert len(lines) == 1  # ONE JSON line
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["metric"] == "summa_gemm_tflops" and line["unit"] == "TFLOP/s" and line["dtype"] == "f64" and line["n_gpus"] == 1
+    assert "workload" in line["config"] and "model" not in line["config"]
+    roof = line["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in roof, key
+    assert roof["bound"] == "tensor" and abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12
+    e2e = line["e2e"]
+    assert e2e["verified"] is True and e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == 3 * 8 * 64 * 64 and e2e["d2h_bytes_per_step"] == 8 * 64 * 64
+    assert line["gpu_launches"] == _Stats.launches * 2
+    assert line["native_fp64_dmma"]["roofline"]["unit"] == "TFLOP/s"  # the second kernel is reported beside the first
+
+
+def test_e2e_leg_refuses_to_report_a_wrong_result(monkeypatch, fake_cuda):
+    capi = _fake_capi(wrong_result=True)
+    e2e = bench.e2e_measure(_args(), capi, capi.load(), 0, (1, 1), 0, 1, lambda: None, lambda x: x)
+    assert e2e["verified"] is False and e2e["value"] is None
+
+
+def test_experimental_variants_change_the_reported_arithmetic(monkeypatch, fake_cuda):
+    import hpc_multigpu_matrixmult_b200 as pkg
+
+    monkeypatch.setattr(pkg, "capi", _fake_capi(), raising=False)
+    monkeypatch.setitem(sys.modules, "hpc_multigpu_matrixmult_b200.capi", pkg.capi)
+    monkeypatch.setenv("PHPC_OZAKI_DIGITS", "balanced")
+    monkeypatch.setenv("PHPC_OZAKI_KERNEL", "2cta")
+    out = io.StringIO()
+    with redirect_stdout(out):
+        bench.product_arm(_args(no_e2e=True, no_secondary=True))
+    line = json.loads([l for l in out.getvalue().splitlines() if l.startswith("{")][0])
+    assert "28 int8 MMAs" in line["roofline"]["note"] and "2cta" in line["roofline"]["kernel"]
+    assert line["roofline"]["ops_per_launch"] == 2.0 * 64 ** 3 * 28
+
+
+def test_reference_arm_line(monkeypatch):
+    monkeypatch.setattr(bench, "run_reference_cpu", lambda n, opt="O0": (1e-3, 2.0, "reference"))
+    monkeypatch.delenv("RANK", raising=False)
+    out = io.StringIO()
+    with redirect_stdout(out):
+        bench.reference_arm(_args(impl="reference"))
+    line = json.loads(out.getvalue().strip())
+    assert line["impl"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "reference"
+    assert line["metric"] == "summa_gemm_tflops" and line["value"] == line["e2e"]["value"] == line["cpu_baseline"]["value"]
+    # ranks other than 0 print nothing
+    monkeypatch.setenv("RANK", "1")
+    out = io.StringIO()
+    with redirect_stdout(out):
+        bench.reference_arm(_args(impl="reference"))
+    assert out.getvalue() == ""
+
+
+def test_e2e_child_prints_one_tagged_json_object(monkeypatch, fake_cuda):
+    import hpc_multigpu_matrixmult_b200 as pkg
+
+    monkeypatch.setattr(pkg, "capi", _fake_capi(), raising=False)
+    monkeypatch.setitem(sys.modules, "hpc_multigpu_matrixmult_b200.capi", pkg.capi)
+    out = io.StringIO()
+    with redirect_stdout(out):
+        bench.e2e_child(_args())
+    tagged = [l for l in out.getvalue().splitlines() if l.startswith("E2E_JSON ")]
+    assert len(tagged) == 1
+    e2e = json.loads(tagged[0][len("E2E_JSON "):])
+    assert e2e["verified"] is True and e2e["unit"] == "TFLOP/s" and "host_row_bands" in e2e
