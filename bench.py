@@ -70,6 +70,29 @@ def run_reference_cpu(n, opt="O0"):
     return 2.0 * n ** 3 / secs / 1e12, secs, kind
 
 
+def run_reference_summa_all_cores(n=4096):
+    """The reference's own SUMMA (src/phpc_summa.c compiled unchanged, oracle/_ref/ref_summa_cpu.out) on as many host
+    cores as it can use: one MPI rank per core (a power of two, at most 16) under the shim, the local GEMM plugin being
+    the CPU restatement of the reference kernel's arithmetic (oracle/ref_cpu_plugin.c; the reference itself only ships a
+    GPU plugin).  Reported beside the single-threaded iterative.c number; returns None if it cannot run here."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_summa_cpu.out")
+    mpirun = os.path.join(ROOT, "bin", "mpirun")
+    if not (os.path.exists(exe) and os.path.exists(mpirun)):
+        return None
+    ranks = 1
+    while ranks * 2 <= min(os.cpu_count() or 1, 16):
+        ranks *= 2
+    try:
+        p = subprocess.run([mpirun, "-n", str(ranks), exe, str(n), "1", "-"], capture_output=True, text=True, timeout=600)
+        f = p.stdout.strip().split(",")
+        secs = float(f[4])
+    except (subprocess.TimeoutExpired, OSError, ValueError, IndexError):
+        return None
+    return {"value": 2.0 * n ** 3 / secs / 1e12, "unit": UNIT, "cores": ranks, "kind": "port", "seconds": secs,
+            "sample": f"reference phpc_summa.c (unchanged) on a {f[2]}x{f[3]} grid of {ranks} MPI-shim ranks, N={n}, CPU gemm_t plugin = "
+                      "restatement of the reference kernel's per-element loop (gcc -O2), host-memory broadcasts included"}
+
+
 def run_reference_cuda_build(n=8192, tile=32, gw=64, gh=64, timeout=300):
     """The reference's OWN CUDA+MPI program on this box: oracle/_ref/ref_main.out = /root/reference/src/{main.c, phpc_summa.c,
     phpc_gemm.cu, utils.c} compiled unchanged against the MPI shim (oracle/Makefile), one rank, one GPU.  It times its CUDA pass
@@ -124,7 +147,8 @@ def reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1000.0 * sum(secs) / len(secs), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"SUMMA GEMM N={args.n} FP64 (bounded CPU sample N={n})", "N": args.n, "sample_N": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "host_cores": os.cpu_count()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "host_cores": os.cpu_count(),
+                         "reference_summa_all_cores": run_reference_summa_all_cores()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -545,6 +569,7 @@ def product_arm(args):
             v3, s3, _ = run_reference_cpu(CPU_SAMPLE_N, "O3")
             cpu["value_O3"] = v3
             cpu["sample"] += f"; same source with -O3: {s3:.3f} s"
+        cpu["reference_summa_all_cores"] = run_reference_summa_all_cores()
 
     ref_cuda = None
     if rank == 0 and world == 1 and not args.no_refcuda:

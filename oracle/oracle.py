@@ -150,5 +150,5 @@ def ref_summa_cpu(N, nranks, fill_kind, workdir):
     out = os.path.join(workdir, f"ref_summa_N{N}_P{nranks}_F{fill_kind}.bin")
     cmd = [os.path.join(root, "bin", "mpirun"), "-n", str(nranks), os.path.join(REF_DIR, "ref_summa_cpu.out"), str(N), str(fill_kind), out]
     res = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=300)
-    n, size, d0, d1 = (int(x) for x in res.stdout.strip().split(","))
+    n, size, d0, d1 = (int(x) for x in res.stdout.strip().split(",")[:4])  # a fifth field is the SUMMA wall time
     return np.fromfile(out, dtype=np.float64).reshape(N, N), (d0, d1)

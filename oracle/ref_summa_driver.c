@@ -3,7 +3,10 @@
  * src/phpc_summa.c, compiled unchanged) under the MPI shim and dumps rank 0's
  * gathered C.  TEST INFRASTRUCTURE ONLY (pins oracle_summa and the shim).
  *
- *   mpirun -n P ref_summa_cpu.out <N> <fill: 0 index | 1 seeded> <out.bin>
+ *   mpirun -n P ref_summa_cpu.out <N> <fill: 0 index | 1 seeded> <out.bin | ->
+ *
+ * Prints "N,P,r,c,seconds" on rank 0: seconds = wall time of the SUMMA call between two barriers (what
+ * bench.py reports as the reference's SUMMA on all host cores); "-" skips the dump of C.
  *
  * Process grid exactly as reference src/main.c:38-62 (MPI_Dims_create, periodic
  * Cartesian grid, reorder 0); C is zeroed first (the reference's main.c does not,
@@ -13,6 +16,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "phpc_summa.h"
 
@@ -39,12 +43,19 @@ int main(int argc, char **argv) {
   oracle_fill(A, N, N, N, 0, 0, N, fill, 1234);
   oracle_fill(B, N, N, N, 0, 0, N, fill, 5678);
   float t = 0;
+  struct timespec t0, t1;
+  MPI_Barrier(MPI_COMM_WORLD);
+  clock_gettime(CLOCK_MONOTONIC, &t0);
   phpc_gemm_summa_cuda(grid, A, B, C, N, 1, 1, 1, 32, &t);
+  MPI_Barrier(MPI_COMM_WORLD);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
   if (rank == 0) {
-    FILE *f = fopen(argv[3], "wb");
-    if (!f || fwrite(C, sizeof(double), (size_t)N * N, f) != (size_t)N * N) MPI_Abort(MPI_COMM_WORLD, 1);
-    fclose(f);
-    printf("%d,%d,%d,%d\n", N, size, dims[0], dims[1]);
+    if (strcmp(argv[3], "-")) {
+      FILE *f = fopen(argv[3], "wb");
+      if (!f || fwrite(C, sizeof(double), (size_t)N * N, f) != (size_t)N * N) MPI_Abort(MPI_COMM_WORLD, 1);
+      fclose(f);
+    }
+    printf("%d,%d,%d,%d,%.6f\n", N, size, dims[0], dims[1], (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
   }
   free(A);
   free(B);

@@ -153,6 +153,7 @@ def test_experimental_variants_change_the_reported_arithmetic(monkeypatch, fake_
 
 def test_reference_arm_line(monkeypatch):
     monkeypatch.setattr(bench, "run_reference_cpu", lambda n, opt="O0": (1e-3, 2.0, "reference"))
+    monkeypatch.setattr(bench, "run_reference_summa_all_cores", lambda n=4096: {"value": 1e-2, "unit": "TFLOP/s", "cores": 8, "kind": "port"})
     monkeypatch.delenv("RANK", raising=False)
     out = io.StringIO()
     with redirect_stdout(out):
@@ -180,3 +181,9 @@ def test_e2e_child_prints_one_tagged_json_object(monkeypatch, fake_cuda):
     assert len(tagged) == 1
     e2e = json.loads(tagged[0][len("E2E_JSON "):])
     assert e2e["verified"] is True and e2e["unit"] == "TFLOP/s" and "host_row_bands" in e2e
+
+
+def test_all_cores_reference_summa_baseline_runs_here(built):
+    """The reference's phpc_summa.c (unchanged) over the MPI shim with the CPU plugin, one rank per core, timed."""
+    out = bench.run_reference_summa_all_cores(n=512)
+    assert out is not None and out["value"] > 0 and out["cores"] >= 1 and out["kind"] == "port"
