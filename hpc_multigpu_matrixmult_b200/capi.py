@@ -82,7 +82,12 @@ _mpi = None
 
 
 def load():
-    """dlopen the MPI shim and the CUDA library (in-tree, built by `make`)."""
+    """dlopen the MPI shim and the CUDA library (in-tree, built by `make`).
+
+    Python hosts that also use torch must `import torch` BEFORE the first call: libphpc_b200.so needs libnccl.so.2 and
+    binds the system's (2.27) when nothing is loaded yet, after which torch's libtorch_cuda.so, which wants the newer
+    libnccl.so.2 bundled in its wheel (2.28, same soname), fails to import.  With torch first, the library binds torch's
+    copy, which is how bench.py runs.  C hosts (bin/main.out) are not affected."""
     global _lib, _mpi
     if _lib is not None:
         return _lib
