@@ -22,6 +22,11 @@
  *   MMA         leader CTA (rank 0) only: tcgen05.mma.cta_group::2, M = 256, N = 128
  *   empty/tfull tcgen05.commit.cta_group::2 ... multicast::cluster, mask 0b11: arrives in both CTAs
  *   tempty      lives in the leader: its 4 epilogue warps arrive locally, the peer's 4 remotely
+ *
+ * Second load path, template parameter TMA (PHPC_OZAKI_KERNEL=2cta-tma): the digit stores are described by tensor
+ * maps (rows of 2 KiB) and every CTA loads with cp.async.bulk.tensor.2d.cta_group::2, whose completion bytes may be
+ * sent to the mbarrier of the PEER CTA: both CTAs' copies complete the LEADER's full[stage] directly (the leader
+ * expects the bytes of both), no relay warp and no peer_full barrier.  Same data, same shared-memory image.
  */
 #pragma once
 #include "ozaki_gemm.cuh"
@@ -85,6 +90,19 @@ __device__ __forceinline__ void umma2_commit_both(uint32_t bar) {
                : "memory");
 }
 
+/* tensor maps of the digit stores, one per pass shape: box = {256 x 8 B = one 2 KiB row, 2*d rows (A) / d rows (B half)} */
+struct StoreMaps {
+  CUtensorMap a[2];
+  CUtensorMap b[2];
+};
+/* the completion bytes go to `leader_bar`, a shared::cluster address that may lie in the other CTA of the pair */
+__device__ __forceinline__ void tma2_load_rows(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int row) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(leader_bar), "r"(0), "r"(row)
+      : "memory");
+}
+
 /* progress word of one warp role: (stage marker << 28) | (units done & 0xfffffff); slot 0 producer, 1 MMA issuer / relay,
  * 2..5 epilogue warps, 6 set-up / tear-down.  Markers: 1 waiting for a barrier, 2 past it, 3 role finished. */
 __device__ __forceinline__ void progress_mark(const Params &p, int slot, uint32_t marker, uint32_t count) {
@@ -96,9 +114,11 @@ __device__ __forceinline__ void progress_mark(const Params &p, int slot, uint32_
 
 /* Params as in ozaki_gemm.cuh with: tiles_m = number of 128-row tiles rounded up to EVEN (TA holds zero digits
  * for the padding tile), TB in half-major order. */
-template <int S_T, bool BAL>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_gemm_2cta_kernel(const Params p) {
+template <int S_T, bool BAL, bool TMA = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+    ozaki_gemm_2cta_kernel(const Params p, const __grid_constant__ StoreMaps maps) {
   static_assert(S_T >= 2 && S_T <= MAX_S, "digit count is a compile-time constant in this kernel");
+  static_assert(!TMA || (S_T + GROUPS_PER_PASS - 1) / GROUPS_PER_PASS <= 2, "two tensor-map shapes: at most two passes");
   constexpr int S = S_T;
   constexpr int DB = BAL ? 8 : DIGIT_BITS;
   constexpr int NPASS = (S + GROUPS_PER_PASS - 1) / GROUPS_PER_PASS;
@@ -165,12 +185,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
             progress_mark(p, 0, 2, loads++);
             const uint32_t full = full0 + 8 * stage;
-            mbar_expect_tx(full, (a_bytes + b_bytes) * nsub);
             const uint32_t sa = smem_base + stage * STAGE2_BYTES;
             const uint32_t sb = sa + MAX_S * SLOT_BYTES;
-            for (int h = 0; h < nsub; ++h) {
-              bulk_load(sa + h * d_hi * SLOT_BYTES, ta + (size_t)(ks + h) * a_step, a_bytes, full);
-              bulk_load(sb + h * d_hi * B_HALF_BYTES, tb + (size_t)(ks + h) * b_step, b_bytes, full);
+            if (TMA) {
+              /* both CTAs' copies complete the LEADER's barrier, which expects the bytes of both */
+              if (leader) mbar_expect_tx(full, 2 * (a_bytes + b_bytes) * nsub);
+              const uint32_t leader_full = map_to_cta(full, 0);
+              for (int h = 0; h < nsub; ++h) {
+                /* store rows are 2 KiB: an A digit tile is 2 rows, a B half tile 1 row */
+                const long long a_row = ((long long)(2 * tm2 + (int)rank) * p.ksteps + (ks + h)) * (2 * S);
+                const long long b_row = (((long long)tn * p.ksteps + (ks + h)) * 2 + (int)rank) * S;
+                tma2_load_rows(sa + h * d_hi * SLOT_BYTES, &maps.a[ps], leader_full, (int)a_row);
+                tma2_load_rows(sb + h * d_hi * B_HALF_BYTES, &maps.b[ps], leader_full, (int)b_row);
+              }
+            } else {
+              mbar_expect_tx(full, (a_bytes + b_bytes) * nsub);
+              for (int h = 0; h < nsub; ++h) {
+                bulk_load(sa + h * d_hi * SLOT_BYTES, ta + (size_t)(ks + h) * a_step, a_bytes, full);
+                bulk_load(sb + h * d_hi * B_HALF_BYTES, tb + (size_t)(ks + h) * b_step, b_bytes, full);
+              }
             }
             if (++stage == STAGES2) {
               stage = 0;
@@ -183,7 +216,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
     }
   } else if (warp == 1 && !leader) {
     /* ===== peer CTA: forward "my operands of this stage have landed" to the leader ===== */
-    if (lane == 0) {
+    if (lane == 0 && !TMA) {
       int stage = 0;
       uint32_t phase = 0, fwd = 0;
       const uint32_t leader_pfull0 = map_to_cta(pfull0, 0);
@@ -227,9 +260,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) ozaki_ge
         for (int ks = 0; ks < p.ksteps; ks += sub) {
           const int nsub = min(sub, p.ksteps - ks);
           if (lane == 0) progress_mark(p, 1, 1, steps);
-          mbar_wait(full0 + 8 * stage, phase);
+          if (TMA)
+            mbar_wait_cluster(full0 + 8 * stage, phase); /* the peer's copies complete this barrier too */
+          else
+            mbar_wait(full0 + 8 * stage, phase);
           if (lane == 0) progress_mark(p, 1, 5, steps);
-          mbar_wait_cluster(pfull0 + 8 * stage, phase);
+          if (!TMA) mbar_wait_cluster(pfull0 + 8 * stage, phase);
           if (lane == 0) progress_mark(p, 1, 2, steps++);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_base + stage * STAGE2_BYTES;

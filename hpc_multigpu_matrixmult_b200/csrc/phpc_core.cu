@@ -206,6 +206,24 @@ static void encode_map_2d(CUtensorMap *map, const double *base, long long inner,
   }
 }
 
+/* A digit store of the Ozaki kernels seen as rows of 2 KiB (256 x 8-byte elements, no swizzle): a box of `box_rows` rows is
+ * one contiguous range, so the tensor-map copy of the experimental 2cta-tma kernel writes the same shared-memory image as
+ * the plain bulk copy of the other kernels. */
+static void encode_store_map(CUtensorMap *map, const void *base, size_t bytes, int box_rows) {
+  PHPC_REQUIRE(bytes % 2048 == 0 && box_rows >= 1 && box_rows <= 256, "digit store is not a whole number of 2 KiB rows");
+  cuuint64_t gdim[2] = {256, (cuuint64_t)(bytes / 2048)};
+  cuuint64_t gstride[1] = {2048};
+  cuuint32_t box[2] = {256, (cuuint32_t)box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "CUresult %d (digit store of %zu bytes, box of %d rows)", (int)r, bytes, box_rows);
+    phpc_die("cuTensorMapEncodeTiled", msg, __FILE__, __LINE__);
+  }
+}
+
 int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                      int k, int n, int ctas, cudaStream_t stream) {
   if (m <= 0 || n <= 0 || k <= 0) return 0; /* C += 0 */
@@ -277,10 +295,12 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
   }
   /* EXPERIMENTAL, opt-in, not validated on hardware in round 1 (tools/ozaki_variants.py validates them):
    *   PHPC_OZAKI_DIGITS=balanced  7 balanced base-256 digits: 28 digit products instead of 36
-   *   PHPC_OZAKI_KERNEL=2cta      CTA pairs, cta_group::2 MMAs with M = 256 (ozaki_gemm2.cuh) */
+   *   PHPC_OZAKI_KERNEL=2cta      CTA pairs, cta_group::2 MMAs with M = 256 (ozaki_gemm2.cuh)
+   *   PHPC_OZAKI_KERNEL=2cta-tma  the same with cp.async.bulk.tensor.cta_group::2 loads instead of the relay warp */
   const char *dg = getenv("PHPC_OZAKI_DIGITS"), *kn = getenv("PHPC_OZAKI_KERNEL");
   const bool balanced = dg && !strcmp(dg, "balanced");
-  const bool two_cta = kn && !strcmp(kn, "2cta");
+  const bool two_cta_tma = kn && !strcmp(kn, "2cta-tma"); /* same kernel, operands loaded through tensor maps (ozaki_gemm2.cuh) */
+  const bool two_cta = two_cta_tma || (kn && !strcmp(kn, "2cta"));
   if (balanced) slices = 7;
   PHPC_REQUIRE(!two_cta || slices == (balanced ? 7 : 8), "the 2-CTA kernel is built for 8 truncated or 7 balanced digits");
   PHPC_REQUIRE(slices >= 2 && slices <= MAX_SLICES, "PHPC_OZAKI_SLICES must be in 2..8");
@@ -356,8 +376,10 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     if (balanced || two_cta) { /* experimental kernels opt in to their shared memory here, not at context creation:
                                 * nothing about them may affect the default path */
       CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<7, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<7, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     }
     if (two_cta) {
       p.tiles_m = tiles_m_store;
@@ -365,10 +387,24 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
       long long clusters = ctx->sm_count / 2;
       if (clusters > pair_tiles) clusters = pair_tiles;
       const int grid2 = (int)(2 * clusters); /* __cluster_dims__(2,1,1): CTAs 2c and 2c+1 form pair c */
-      if (balanced)
-        ozaki_gemm_2cta_kernel<7, true><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p);
-      else
-        ozaki_gemm_2cta_kernel<8, false><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p);
+      StoreMaps maps;
+      memset(&maps, 0, sizeof maps);
+      if (two_cta_tma) {
+        const size_t a_bytes = (size_t)slices * m_pad * kp, b_bytes = (size_t)slices * n_pad * kp;
+        for (int ps = 0; ps < 2; ++ps) { /* pass 0 stages every digit, pass 1 the first slices - 4 */
+          const int d = ps == 0 ? slices : slices - GROUPS_PER_PASS;
+          encode_store_map(&maps.a[ps], TA, a_bytes, 2 * d);
+          encode_store_map(&maps.b[ps], TB, b_bytes, d);
+        }
+        if (balanced)
+          ozaki_gemm_2cta_kernel<7, true, true><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p, maps);
+        else
+          ozaki_gemm_2cta_kernel<8, false, true><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p, maps);
+      } else if (balanced) {
+        ozaki_gemm_2cta_kernel<7, true, false><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p, maps);
+      } else {
+        ozaki_gemm_2cta_kernel<8, false, false><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p, maps);
+      }
     } else {
       int grid = ctx->sm_count;
       if ((long long)grid > tiles) grid = (int)tiles;

@@ -1,9 +1,9 @@
 """Model check of the synchronisation protocol of the experimental 2-CTA Ozaki kernel (csrc/ozaki_gemm2.cuh).
 
 The kernel has not run on hardware yet, and its risk is not the arithmetic (shared with the validated 1-CTA kernel) but
-the plumbing between the two CTAs of a pair: per-CTA full barriers, the peer's relay warp, multicast commits, the tempty
-barrier that lives in the leader.  This test restates that plumbing — the loops of the five warp roles, line for line,
-with mbarrier semantics (arrival counts, transaction bytes, phase parity), asynchronous bulk copies that land in any
+the plumbing between the two CTAs of a pair: per-CTA full barriers, the peer's relay warp (or, on the tensor-map load path,
+both CTAs' copies completing the leader's barrier), multicast commits, the tempty barrier that lives in the leader.
+This test restates that plumbing — the loops of the five warp roles, line for line, with mbarrier semantics (arrival counts, transaction bytes, phase parity), asynchronous bulk copies that land in any
 order, MMAs that execute in issue order some time after they were issued, and commits that arrive once all earlier
 MMAs are done — and runs it under many random interleavings.  It asserts
   * no deadlock: every role of both CTAs finishes;
@@ -56,8 +56,8 @@ class Cta:
 
 
 class Sim:
-    def __init__(self, S, ksteps, tiles, seed):
-        self.S, self.ksteps, self.tiles = S, ksteps, tiles
+    def __init__(self, S, ksteps, tiles, seed, tma=False):
+        self.S, self.ksteps, self.tiles, self.tma = S, ksteps, tiles, tma
         self.npass = (S + GROUPS_PER_PASS - 1) // GROUPS_PER_PASS
         self.cta = [Cta(), Cta()]
         self.rng = random.Random(seed)
@@ -84,10 +84,16 @@ class Sim:
                     nsub = min(sub, self.ksteps - ks)
                     yield ("wait", me.empty[stage], phase ^ 1)
                     a_bytes, b_bytes = d_hi * 4096, d_hi * 2048
-                    me.full[stage].expect_tx((a_bytes + b_bytes) * nsub)
+                    if self.tma:  # cp.async.bulk.tensor.cta_group::2: both CTAs' bytes complete the LEADER's barrier
+                        if rank == 0:
+                            me.full[stage].expect_tx(2 * (a_bytes + b_bytes) * nsub)
+                        signal = 0
+                    else:
+                        me.full[stage].expect_tx((a_bytes + b_bytes) * nsub)
+                        signal = rank
                     for h in range(nsub):
-                        self.loads.append((rank, stage, ("A", h), (tile, ps, ks + h), a_bytes))
-                        self.loads.append((rank, stage, ("B", h), (tile, ps, ks + h), b_bytes))
+                        self.loads.append((rank, stage, ("A", h), (tile, ps, ks + h), a_bytes, signal))
+                        self.loads.append((rank, stage, ("B", h), (tile, ps, ks + h), b_bytes, signal))
                     yield ("step",)
                     stage += 1
                     if stage == STAGES:
@@ -97,7 +103,7 @@ class Sim:
     def relay(self):  # warp 1 of the peer CTA
         me, leader = self.cta[1], self.cta[0]
         stage, phase = 0, 0
-        for tile in range(self.tiles):
+        for tile in range(0 if self.tma else self.tiles):  # the tensor-map path needs no relay
             for ps in range(self.npass):
                 _, _, _, sub = self.pass_shape(ps)
                 for ks in range(0, self.ksteps, sub):
@@ -119,7 +125,8 @@ class Sim:
                 for ks in range(0, self.ksteps, sub):
                     nsub = min(sub, self.ksteps - ks)
                     yield ("wait", me.full[stage], phase)
-                    yield ("wait", me.pfull[stage], phase)
+                    if not self.tma:
+                        yield ("wait", me.pfull[stage], phase)
                     for h in range(nsub):
                         first = (ks + h) > 0
                         for gi in range(GROUPS_PER_PASS):
@@ -158,9 +165,9 @@ class Sim:
 
     # ---- asynchronous hardware ----
     def land_a_load(self):
-        rank, stage, part, tag, nbytes = self.loads.pop(self.rng.randrange(len(self.loads)))
+        rank, stage, part, tag, nbytes, signal = self.loads.pop(self.rng.randrange(len(self.loads)))
         self.cta[rank].smem[stage][part] = tag
-        self.cta[rank].full[stage].complete_tx(nbytes)
+        self.cta[signal].full[stage].complete_tx(nbytes)
 
     def run_tensor_op(self):
         op = self.tensor.pop(0)
@@ -221,11 +228,12 @@ class Sim:
         assert not self.loads and not self.tensor
 
 
+@pytest.mark.parametrize("tma", [False, True])
 @pytest.mark.parametrize("S", [8, 7])
 @pytest.mark.parametrize("ksteps,tiles", [(4, 1), (4, 3), (8, 2), (12, 2)])
-def test_protocol_under_random_interleavings(S, ksteps, tiles):
+def test_protocol_under_random_interleavings(S, ksteps, tiles, tma):
     for seed in range(25):
-        Sim(S, ksteps, tiles, seed).run()
+        Sim(S, ksteps, tiles, seed, tma).run()
 
 
 def test_the_model_catches_a_missing_relay():

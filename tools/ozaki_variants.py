@@ -8,6 +8,7 @@ For each variant (environment of phpc_launch_ozaki, csrc/phpc_core.cu)
     balanced           PHPC_OZAKI_DIGITS=balanced                      7 balanced base-256 digits, 28 products
     2cta               PHPC_OZAKI_KERNEL=2cta                          CTA pairs, cta_group::2, M = 256
     2cta+balanced      both
+    2cta-tma[+balanced] PHPC_OZAKI_KERNEL=2cta-tma                     the 2-CTA kernel loading through tensor maps (no relay warp)
     ...+kc16384        PHPC_OZ_KC=16384                                K chunks of 16384: half as many epilogues
 a child process (bounded by a timeout: a hanging kernel must not take the GPU box with it) checks the variant
 against the native-FP64 DMMA kernel on the same device inputs over shapes that exercise odd tile counts (the
@@ -29,6 +30,9 @@ VARIANTS = {
     "balanced": {"PHPC_OZAKI_DIGITS": "balanced"},
     "2cta": {"PHPC_OZAKI_KERNEL": "2cta", "PHPC_OZ_PROGRESS": "1"},
     "2cta+balanced": {"PHPC_OZAKI_KERNEL": "2cta", "PHPC_OZAKI_DIGITS": "balanced", "PHPC_OZ_PROGRESS": "1"},
+    # the 2-CTA kernel with cp.async.bulk.tensor.cta_group::2 loads instead of the relay warp
+    "2cta-tma": {"PHPC_OZAKI_KERNEL": "2cta-tma", "PHPC_OZ_PROGRESS": "1"},
+    "2cta-tma+balanced": {"PHPC_OZAKI_KERNEL": "2cta-tma", "PHPC_OZAKI_DIGITS": "balanced", "PHPC_OZ_PROGRESS": "1"},
     # K chunks of 16384 instead of 8192 (int32 stays exact up to 16643 / 18724): half as many epilogues per GEMM
     "default+kc16384": {"PHPC_OZ_KC": "16384"},
     "2cta+balanced+kc16384": {"PHPC_OZAKI_KERNEL": "2cta", "PHPC_OZAKI_DIGITS": "balanced", "PHPC_OZ_KC": "16384", "PHPC_OZ_PROGRESS": "1"},
