@@ -468,11 +468,9 @@ def product_arm(args):
     s.fill(capi.FILL_SEEDED)
     stream = torch.cuda.current_stream()
     sptr = ctypes.c_void_p(stream.cuda_stream)
-    balanced = os.environ.get("PHPC_OZAKI_DIGITS") == "balanced"  # experimental variants of phpc_launch_ozaki (opt-in)
-    two_cta = os.environ.get("PHPC_OZAKI_KERNEL") == "2cta"
-    slices = 7 if balanced else int(os.environ.get("PHPC_OZAKI_SLICES", "8"))
-    pairs = slices * (slices + 1) // 2
-    oz_kernel = (f"phpc::oz::ozaki_gemm_2cta_kernel<{slices}> (tcgen05.mma.cta_group::2 kind::i8, M=256 per CTA pair" if two_cta
+    oz = capi.ozaki_config()  # what the library's tcgen05 path runs with in this process (environment, else its defaults)
+    slices, pairs, balanced, two_cta = oz["digits"], oz["products"], oz["balanced"], oz["kernel"] != "1cta"
+    oz_kernel = (f"phpc::oz::ozaki_gemm_2cta_kernel<{slices}> [{oz['kernel']}] (tcgen05.mma.cta_group::2 kind::i8, M=256 per CTA pair" if two_cta
                  else f"phpc::oz::ozaki_gemm_kernel<{slices}> (tcgen05.mma kind::i8") + ", int32 accumulators in TMEM, cp.async.bulk ring)"
     fp64_pk, fp64_src = fp64_peak()
     int8_pk, int8_src = int8_peak()

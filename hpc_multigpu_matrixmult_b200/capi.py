@@ -253,6 +253,13 @@ def summa_schedule(N, r, c, pi, pj, kc=0):
     return list(steps), m.value, n.value
 
 
+def ozaki_config():
+    """What the tcgen05 (Ozaki) path of this process runs with: environment, else the library's defaults."""
+    v = [ctypes.c_int() for _ in range(4)]
+    load().phpc_ozaki_config(*[ctypes.byref(x) for x in v])
+    return {"digits": v[0].value, "products": v[1].value, "kernel": ("1cta", "2cta", "2cta-tma")[v[2].value], "balanced": bool(v[3].value)}
+
+
 def host_plan(m, nsteps, bands, align=128):
     """Operation list of the band-pipelined host-sourced run (pure host arithmetic, no GPU)."""
     L = load()

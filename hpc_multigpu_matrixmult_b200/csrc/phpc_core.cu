@@ -257,6 +257,41 @@ int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const doub
 /* Bring-up aid of the experimental 2-CTA kernel (PHPC_OZ_PROGRESS=1): 8 host-mapped words per CTA in which every
  * warp role records how far it got (ozaki_gemm2.cuh, progress_mark).  The host can read them while a kernel hangs:
  * tools/ozaki_variants.py launches, polls phpc_compute_stream_idle() and dumps phpc_oz_progress_read() on a timeout. */
+/* Which digit scheme and kernel phpc_launch_ozaki uses: the environment, else the built-in default.  The defaults are
+ * the round-1 kernel (8 truncated 7-bit digits, 1-CTA); flipping them after the variants have been validated on
+ * hardware is a change of these two strings. */
+#define PHPC_OZAKI_DEFAULT_DIGITS "trunc" /* "trunc" | "balanced" */
+#define PHPC_OZAKI_DEFAULT_KERNEL "1cta"  /* "1cta" | "2cta" | "2cta-tma" */
+struct OzakiChoice {
+  bool balanced;
+  int kernel; /* 0 = 1-CTA, 1 = 2-CTA with relay warp, 2 = 2-CTA with tensor-map loads */
+};
+static OzakiChoice ozaki_choice() {
+  const char *dg = getenv("PHPC_OZAKI_DIGITS"), *kn = getenv("PHPC_OZAKI_KERNEL");
+  if (!dg || !*dg) dg = PHPC_OZAKI_DEFAULT_DIGITS;
+  if (!kn || !*kn) kn = PHPC_OZAKI_DEFAULT_KERNEL;
+  OzakiChoice c;
+  PHPC_REQUIRE(!strcmp(dg, "trunc") || !strcmp(dg, "balanced"), "PHPC_OZAKI_DIGITS must be trunc or balanced");
+  PHPC_REQUIRE(!strcmp(kn, "1cta") || !strcmp(kn, "2cta") || !strcmp(kn, "2cta-tma"), "PHPC_OZAKI_KERNEL must be 1cta, 2cta or 2cta-tma");
+  c.balanced = !strcmp(dg, "balanced");
+  c.kernel = !strcmp(kn, "2cta") ? 1 : (!strcmp(kn, "2cta-tma") ? 2 : 0);
+  return c;
+}
+/* What the Ozaki path of this process computes with (for bench.py's description of the arithmetic): digits per operand,
+ * int8 digit products per FP64 product, kernel (0 / 1 / 2 as above), balanced base-256 digits or truncated 7-bit ones. */
+extern "C" void phpc_ozaki_config(int *digits, int *products, int *kernel, int *balanced) {
+  const OzakiChoice c = ozaki_choice();
+  int s = 7;
+  if (!c.balanced) {
+    const char *e = getenv("PHPC_OZAKI_SLICES");
+    s = (e && *e) ? atoi(e) : 8;
+  }
+  if (digits) *digits = s;
+  if (products) *products = s * (s + 1) / 2;
+  if (kernel) *kernel = c.kernel;
+  if (balanced) *balanced = c.balanced ? 1 : 0;
+}
+
 static unsigned int *g_oz_progress = nullptr;
 static int g_oz_progress_words = 0;
 static unsigned int *oz_progress_buffer(int ctas) {
@@ -297,10 +332,10 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
    *   PHPC_OZAKI_DIGITS=balanced  7 balanced base-256 digits: 28 digit products instead of 36
    *   PHPC_OZAKI_KERNEL=2cta      CTA pairs, cta_group::2 MMAs with M = 256 (ozaki_gemm2.cuh)
    *   PHPC_OZAKI_KERNEL=2cta-tma  the same with cp.async.bulk.tensor.cta_group::2 loads instead of the relay warp */
-  const char *dg = getenv("PHPC_OZAKI_DIGITS"), *kn = getenv("PHPC_OZAKI_KERNEL");
-  const bool balanced = dg && !strcmp(dg, "balanced");
-  const bool two_cta_tma = kn && !strcmp(kn, "2cta-tma"); /* same kernel, operands loaded through tensor maps (ozaki_gemm2.cuh) */
-  const bool two_cta = two_cta_tma || (kn && !strcmp(kn, "2cta"));
+  OzakiChoice choice = ozaki_choice();
+  const bool balanced = choice.balanced;
+  const bool two_cta_tma = choice.kernel == 2; /* same kernel, operands loaded through tensor maps (ozaki_gemm2.cuh) */
+  const bool two_cta = choice.kernel != 0;
   if (balanced) slices = 7;
   PHPC_REQUIRE(!two_cta || slices == (balanced ? 7 : 8), "the 2-CTA kernel is built for 8 truncated or 7 balanced digits");
   PHPC_REQUIRE(slices >= 2 && slices <= MAX_SLICES, "PHPC_OZAKI_SLICES must be in 2..8");

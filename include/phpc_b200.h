@@ -91,6 +91,12 @@ void phpc_fill_device(double *d, long long ld, long long rows, long long cols, l
 void phpc_fill_host(double *h, long long ld, long long rows, long long cols, long long row0, long long col0, long long N, int kind,
                     unsigned long long seed);
 
+/* The configuration the tcgen05 (Ozaki) path of this process runs with (environment PHPC_OZAKI_DIGITS / PHPC_OZAKI_KERNEL /
+ * PHPC_OZAKI_SLICES, else the built-in defaults): digits per operand, int8 digit products per FP64 product
+ * (digits*(digits+1)/2), kernel 0 = 1-CTA, 1 = 2-CTA (relay), 2 = 2-CTA (tensor-map loads), balanced = 1 for balanced
+ * base-256 digits (0: truncated 7-bit digits).  Any pointer may be NULL. */
+void phpc_ozaki_config(int *digits, int *products, int *kernel, int *balanced);
+
 /* ---- bring-up diagnostics of the experimental 2-CTA kernel (PHPC_OZAKI_KERNEL=2cta, PHPC_OZ_PROGRESS=1) ---- */
 /* 1 when everything enqueued on the library's compute stream has finished, 0 while work is pending (never blocks). */
 int phpc_compute_stream_idle(void);

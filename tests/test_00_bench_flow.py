@@ -59,6 +59,15 @@ def _fake_capi(wrong_result=False):
 
     lib.phpc_fill_host = fill_host
     m.load = lambda: lib
+
+    def ozaki_config():
+        import os
+
+        bal = os.environ.get("PHPC_OZAKI_DIGITS") == "balanced"
+        d = 7 if bal else 8
+        return {"digits": d, "products": d * (d + 1) // 2, "kernel": os.environ.get("PHPC_OZAKI_KERNEL", "1cta"), "balanced": bal}
+
+    m.ozaki_config = ozaki_config
     m.mpi_init = lambda *a: None
     m.cart_create = lambda dims: 0
     m.Summa = _FakeSumma
