@@ -203,3 +203,25 @@ def test_all_cores_reference_summa_baseline_runs_here(built):
     """The reference's phpc_summa.c (unchanged) over the MPI shim with the CPU plugin, one rank per core, timed."""
     out = bench.run_reference_summa_all_cores(n=512)
     assert out is not None and out["value"] > 0 and out["cores"] >= 1 and out["kind"] == "port"
+
+
+def test_a_throttled_measurement_is_taken_again(monkeypatch, fake_cuda):
+    import hpc_multigpu_matrixmult_b200 as pkg
+
+    monkeypatch.setattr(pkg, "capi", _fake_capi(), raising=False)
+    monkeypatch.setitem(sys.modules, "hpc_multigpu_matrixmult_b200.capi", pkg.capi)
+    calls = []
+
+    def stop(self, t0, t1):
+        calls.append(1)
+        reasons = ["hw_thermal_slowdown"] if len(calls) == 1 else ["sw_power_cap"]
+        return {"sm_mhz": 1400.0, "sm_max_mhz": 1965.0, "power_w_max": 990.0, "samples": 5, "reasons": reasons}
+
+    monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
+    monkeypatch.setattr(bench.ClockSampler, "stop", stop)
+    out = io.StringIO()
+    with redirect_stdout(out):
+        bench.product_arm(_args(no_e2e=True, no_secondary=True))
+    line = json.loads([l for l in out.getvalue().splitlines() if l.startswith("{")][0])
+    assert line["clocks"]["reasons"] == ["sw_power_cap"]  # the kept measurement; power capping is normal and only noted
+    assert line["clocks"]["remeasured_after"]["reasons"] == ["hw_thermal_slowdown"]
