@@ -122,7 +122,11 @@ void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *stream, phpc_sum
 int phpc_summa_timeline(phpc_summa *s, float *start_ms, float *dur_ms, int max_steps);
 /* Host-sourced run (what phpc_gemm_summa_cuda does): C += A*B on FULL N x N host matrices,
  * owned chunks uploaded on a copy stream while earlier chunks compute, C block downloaded
- * (and gathered to rank 0 when gather != 0) at the end.  Synchronous. */
+ * (and gathered to rank 0 when gather != 0) at the end.  Synchronous.
+ * On a 1 x 1 grid with a block of >= 8192 rows (or PHPC_HOST_BANDS > 1) the C block travels in row
+ * bands under the GEMMs instead (phpc_host_plan above); results are bit-identical to the chunk loop.
+ * Page-locked host matrices (phpc_host_register) are what lets the transfers overlap; pageable memory
+ * works and gives the same results, but the CUDA runtime serialises such copies with the host thread. */
 void phpc_summa_run_host(phpc_summa *s, int backend, int ctas, const double *A, const double *B, double *C, int gather,
                          phpc_summa_stats *stats);
 /* Drop the device blocks cached by phpc_gemm_summa_cuda / phpc_gemm_summa_cublas. */
