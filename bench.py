@@ -248,6 +248,22 @@ def int8_sustained_peak():
     return best
 
 
+def ozaki_traffic(m, k, n):
+    """DRAM bytes of one Ozaki GEMM launch of this shape from an `ncu --set full` capture, if one is committed:
+    profiles/ozaki_traffic*.json written by tools/ncu_summary.py --traffic-json --shape m,k,n (scripts/gpu_session.sh)."""
+    import glob
+
+    hit = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "ozaki_traffic*.json"))):
+        try:
+            d = json.load(open(path))
+            if d.get("shape_mkn") == [int(m), int(k), int(n)]:
+                hit = (d["dram_bytes"], os.path.relpath(path, ROOT), d.get("kernel"))
+        except (OSError, ValueError, KeyError):
+            continue
+    return hit
+
+
 def measured_peaks():
     """MEASURED_PEAKS.json (driver-written on this pool: HBM copy GB/s, cuBLAS bf16 burst / sustained TFLOP/s), or None."""
     try:
@@ -511,6 +527,14 @@ def product_arm(args):
                     "traffic_note": "no ncu --set full capture of this launch shape yet; the N=8192 launch of the same kernel family read 11.5 GB "
                                     "and wrote 1.1 GB of DRAM (algorithmic: 1.07 GB of digits + 2 passes x 1.07 GB of C) = 8.5 % of HBM peak, "
                                     "profiles/ncu_ozaki_gemm_n8192_r01_v3.txt"}
+            k_launch = min(int(k_per_gemm), int(os.environ.get("PHPC_OZ_KC", "8192")))  # the launcher cuts K into chunks of this size
+            tr = ozaki_traffic(m_blk, k_launch, n_blk)
+            if tr:
+                roof["traffic"] = tr[0]
+                roof["traffic_source"] = (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of {tr[2]} at m,k,n = "
+                                          f"{m_blk},{k_launch},{n_blk} ({tr[1]}); algorithmic bytes of that launch: "
+                                          f"{(m_blk + n_blk) * k_launch * slices + 4 * 8 * m_blk * n_blk} (digits read once + 2 passes of C read+write)")
+                roof.pop("traffic_note", None)
             sus = int8_sustained_peak()
             if sus:
                 roof["peak_sustained"] = sus[0]

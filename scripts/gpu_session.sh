@@ -23,7 +23,10 @@ for s in $STAGES; do
     ncu)      run ncu_launches 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
                   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-refcuda --no-secondary > gpurun_out/ncu_bench.log 2>&1
               run ncu_full 900 ncu --set full --clock-control none --import-source on -k regex:ozaki_gemm -s 1 -c 1 -o gpurun_out/prof_ozaki_bench_shape -f \
-                  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-refcuda --no-secondary > gpurun_out/ncu_full.log 2>&1 ;;
+                  python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-refcuda --no-secondary > gpurun_out/ncu_full.log 2>&1
+              # back in the build container: python tools/ncu_summary.py gpurun_out/prof_ozaki_bench_shape.ncu-rep \
+              #     --traffic-json profiles/ozaki_traffic_rNN.json --shape 32768,8192,32768 > profiles/ncu_ozaki_bench_shape_rNN.txt
+              ;;
     bench)    run bench 1500 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench.err; tail -c 1500 gpurun_out/bench_n1.json ;;
   esac
 done
