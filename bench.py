@@ -410,7 +410,7 @@ def e2e_in_child(args):
     note = None
     for env in attempts:
         try:
-            p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1500)
+            p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=420)
             lines = [l for l in p.stdout.splitlines() if l.startswith("E2E_JSON ")]
             if p.returncode == 0 and lines:
                 out = json.loads(lines[-1][len("E2E_JSON "):])
