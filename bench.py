@@ -239,12 +239,16 @@ def int8_sustained_peak():
     best = None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "umma_rate_sustained*.jsonl"))):
         try:
-            for l in open(path):
-                d = json.loads(l)
-                if d.get("operands") == "random" and "chip_tops_sustained" in d:
-                    best = (d["chip_tops_sustained"], os.path.relpath(path, ROOT))
-        except (OSError, ValueError):
+            lines = open(path).read().splitlines()
+        except OSError:
             continue
+        for l in lines:
+            try:
+                d = json.loads(l)
+            except ValueError:
+                continue  # a stray non-JSON line must not hide the measurement
+            if isinstance(d, dict) and d.get("operands") == "random" and "chip_tops_sustained" in d:
+                best = (d["chip_tops_sustained"], os.path.relpath(path, ROOT))
     return best
 
 

@@ -12,7 +12,7 @@ set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 STAGES="${STAGES:-tests variants peaks ncu bench}"
-run() { local name=$1 limit=$2; shift 2; echo "=== $name"; timeout "$limit" "$@"; echo "=== $name exit $?"; }
+run() { local name=$1 limit=$2; shift 2; echo "=== $name" >&2; timeout "$limit" "$@"; echo "=== $name exit $?" >&2; }  # markers on stderr: stdout may be a data file
 for s in $STAGES; do
   case $s in
     tests)    run tests 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log ;;
