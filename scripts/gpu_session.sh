@@ -15,7 +15,7 @@ STAGES="${STAGES:-tests variants peaks ncu bench}"
 run() { local name=$1 limit=$2; shift 2; echo "=== $name" >&2; timeout "$limit" "$@"; echo "=== $name exit $?" >&2; }  # markers on stderr: stdout may be a data file
 for s in $STAGES; do
   case $s in
-    tests)    run tests 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log ;;
+    tests)    run tests 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log ;;
     variants) run variants 900 python tools/ozaki_variants.py --out gpurun_out/ozaki_variants.jsonl ;;
     peaks)    run umma_random 120 env UMMA_RANDOM=1 bin/umma_rate > gpurun_out/umma_rate_random.jsonl 2> gpurun_out/umma_rate.err
               run umma_sustain 120 env UMMA_SUSTAIN=1 bin/umma_rate > gpurun_out/umma_rate_sustained.jsonl 2>> gpurun_out/umma_rate.err
