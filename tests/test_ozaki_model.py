@@ -107,3 +107,26 @@ def test_balanced_base256_digits_keep_the_accuracy_with_28_products(oracle):
     assert np.array_equal(om.gemm_balanced(ai, ai, S=7), oracle.index_fill_exact(32))
     d = om.split_digits_balanced(a, om.exponents(a, 1), 1, 7)
     assert all(x.min() >= -128 and x.max() <= 127 for x in d)
+
+
+def test_error_is_normwise_per_row_and_column_not_componentwise(oracle):
+    """What the fixed-digit scheme guarantees and what it does not ("Error model").  Digits are cut
+    below the ROW (column) maximum, so an element 2^-66 of its row's maximum has no digit left: a C element that consists
+    only of such products comes out as 0.  The absolute error still obeys the normwise bound
+    k * 2^-53 * max|A_i| * max|B_j| (far below FP64 rounding of anything else in that row), but the componentwise bound of
+    a native FP64 dot product, ~ k * 2^-53 * sum|a||b|, does not hold for such an element.  The native-FP64 kernel
+    (PHPC_GEMM=dmma) is the path for inputs with that much dynamic range inside single rows/columns."""
+    k = 64
+    a = np.full((2, k), 1e-20)
+    a[0, 0] = 1.0
+    a[1, :] = np.linspace(0.5, 1.0, k)
+    b = np.ones((k, 2))
+    b[0, 0] = 0.0
+    exact = np.array([[float(sum(Fraction(float(a[i, q])) * Fraction(float(b[q, j])) for q in range(k))) for j in range(2)] for i in range(2)])
+    for got in (om.gemm(a, b, S=8), om.gemm_balanced(a, b, S=7)):
+        assert exact[0, 0] > 0 and got[0, 0] == 0.0  # 63 products of 1e-20 * 1: below the last digit of a row whose maximum is 1
+        norm_bound = k * 2.0 ** -53 * np.outer(np.abs(a).max(axis=1), np.abs(b).max(axis=0)) + 2.0 ** -51 * np.abs(exact)
+        assert np.all(np.abs(got - exact) <= norm_bound)
+        comp_bound = 4.0 * np.sqrt(k) * 2.0 ** -53 * (np.abs(a) @ np.abs(b))
+        assert abs(got[0, 0] - exact[0, 0]) > comp_bound[0, 0]
+        assert np.all(np.abs(got[1] - exact[1]) <= comp_bound[1])  # rows without that dynamic range meet the componentwise bound too
