@@ -111,3 +111,27 @@ def test_config5_n30000_tile_width_sweep_1x2(gpu, tmp_path, tile_width):
     assert res.returncode == 0, res.stdout + res.stderr
     rec = open(tmp_path / "csv" / f"cfg5_N30000_T2_G1_TW{tile_width}_GW1_GH1.csv").read().strip().split(",")
     assert rec[0] == "30000" and rec[1] == "2" and float(rec[6]) > 0
+
+
+@pytest.mark.parametrize("gpus", [2, 3])
+def test_gemm_cuda_column_split_over_local_gpus(gpu, capi, oracle, gpus):
+    """phpc_gemm_cuda(..., gpu_count > 1): the reference replicates A and slices B and C by columns over the local GPUs,
+    dev_n = n/g + (gpu < n%g) (src/phpc_gemm.cu:97-129).  Same split here, one in-process call, n not divisible by g."""
+    _need(gpu, gpus)
+    m, k, n = 260, 190, 301  # 301 = 2*150 + 1 = 3*100 + 1: uneven slices on 2 and on 3 GPUs
+    a = oracle.fill(m, k, kind=1, seed=71)
+    b = oracle.fill(k, n, kind=1, seed=72)
+    c0 = oracle.fill(m, n, kind=1, seed=73)
+    want = oracle.gemm_block(a, b, c0)
+    c = c0.copy()
+    secs = capi.phpc_gemm_cuda(a, b, c, gpus, 1, 1, 32)
+    assert secs > 0.0  # mean over the GPUs of the kernel event time (reference :145)
+    assert oracle.rel_frobenius(c, want) <= 1e-14
+    one = c0.copy()
+    capi.phpc_gemm_cuda(a, b, one, 1, 1, 1, 32)
+    assert np.array_equal(c, one)  # a column split does not change any element's arithmetic
+    ai = oracle.fill(128, 128, kind=0)
+    ci = np.zeros((128, 128))
+    capi.phpc_gemm_cuda(ai, ai.copy(), ci, gpus, 1, 1, 32)
+    assert np.array_equal(ci, oracle.index_fill_exact(128))
+    gpu.phpc_b200_set_device(0)
