@@ -22,6 +22,7 @@
 #include "../../include/phpc_b200.h"
 #include "../../include/phpc_gemm.cuh"
 #include "../../include/phpc_summa.h"
+#include "host_band_exec.h"
 #include "phpc_internal.h"
 
 #define NCCL_CHECK(call)                                                            \
@@ -94,47 +95,10 @@ extern "C" int phpc_summa_schedule(int N, int r, int c, int pi, int pj, int kc, 
   return count;
 }
 
-/* Band pipeline of the host-sourced run on one GPU (see phpc_host_op in phpc_summa.h).  Issue order:
- * per band  upload C band, upload its A windows (band 0 also brings every B chunk, interleaved so the
- * first GEMM can start after one chunk), then the GEMMs of the band over all K chunks in ascending K
- * (the per-element summation order is the reference's, src/phpc_gemm.cu:33-52), then the download. */
+/* Operation list of the band-pipelined host-sourced run on one GPU (phpc_host_op in phpc_summa.h): pure arithmetic,
+ * shared with the CPU test of the executor through host_band_exec.h. */
 extern "C" int phpc_host_plan(int m, int nsteps, int bands, int align, phpc_host_op *ops, int max_ops) {
-  if (m <= 0 || nsteps <= 0) return 0;
-  if (bands < 1) bands = 1;
-  if (align < 1) align = 1;
-  int rows_per_band = (m + bands - 1) / bands;
-  rows_per_band = (rows_per_band + align - 1) / align * align;
-  int count = 0;
-  auto emit = [&](int kind, int stream, int band, int step, int row0, int rows, int d0, int d1, int d2) {
-    if (ops && count < max_ops) {
-      phpc_host_op *o = &ops[count];
-      o->kind = kind;
-      o->stream = stream;
-      o->band = band;
-      o->step = step;
-      o->row0 = row0;
-      o->rows = rows;
-      o->ndeps = 0;
-      const int d[3] = {d0, d1, d2};
-      for (int i = 0; i < 3; ++i)
-        if (d[i] >= 0) o->deps[o->ndeps++] = d[i];
-      for (int i = o->ndeps; i < 3; ++i) o->deps[i] = -1;
-    }
-    return count++;
-  };
-  std::vector<int> up_b(nsteps, -1), up_a(nsteps, -1);
-  for (int band = 0, row0 = 0; row0 < m; ++band, row0 += rows_per_band) {
-    const int rows = (m - row0 < rows_per_band) ? m - row0 : rows_per_band;
-    const int up_c = emit(PHPC_HOP_UPLOAD_C, 0, band, -1, row0, rows, -1, -1, -1);
-    for (int q = 0; q < nsteps; ++q) {
-      up_a[q] = emit(PHPC_HOP_UPLOAD_A, 0, band, q, row0, rows, -1, -1, -1);
-      if (band == 0) up_b[q] = emit(PHPC_HOP_UPLOAD_B, 0, -1, q, 0, 0, -1, -1, -1);
-    }
-    int last = -1;
-    for (int q = 0; q < nsteps; ++q) last = emit(PHPC_HOP_GEMM, 1, band, q, row0, rows, q == 0 ? up_c : -1, up_a[q], band == 0 ? up_b[q] : -1);
-    emit(PHPC_HOP_DOWNLOAD_C, 2, band, -1, row0, rows, last, -1, -1);
-  }
-  return count;
+  return phpc::host_plan(m, nsteps, bands, align, ops, max_ops);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -687,91 +651,95 @@ static int launch_local_gemm(phpc_summa *s, int backend, int ctas, const double 
   return phpc_launch_dmma(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, ctas, st);
 }
 
-/* Executes the operation list of phpc_host_plan: one CUDA stream per plan stream, one event per
- * operation that somebody depends on.  The list is verified on the CPU (tests/test_host_plan.py:
- * every conflicting pair of operations is ordered, every legal execution order gives C + A*B). */
+/* CUDA side of phpc::band_execute (host_band_exec.h): plan stream -> CUDA stream, one event per dependency, timing
+ * events around every local GEMM.  The walk over the operation list, with all its pointer arithmetic, is the shared
+ * header and runs on the CPU in tests/test_band_executor.py (deferred streams in random order, host buffers as HBM). */
+struct CudaBandBackend {
+  phpc_summa *s;
+  int backend, ctas;
+  cudaStream_t streams[3];
+  std::vector<cudaEvent_t> deps, g0, g1;
+};
+static void cb_copy2d(void *self, int stream, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width_bytes,
+                      size_t rows, int host_to_device) {
+  CudaBandBackend *b = (CudaBandBackend *)self;
+  CUDA_CHECK(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows,
+                               host_to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, b->streams[stream]));
+}
+static void *cb_record(void *self, int stream) {
+  CudaBandBackend *b = (CudaBandBackend *)self;
+  cudaEvent_t e;
+  CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventRecord(e, b->streams[stream]));
+  b->deps.push_back(e);
+  return (void *)e;
+}
+static void cb_wait(void *self, int stream, void *event) {
+  CudaBandBackend *b = (CudaBandBackend *)self;
+  PHPC_REQUIRE(event != nullptr, "host plan dependency does not point at an earlier, recorded operation");
+  CUDA_CHECK(cudaStreamWaitEvent(b->streams[stream], (cudaEvent_t)event, 0));
+}
+static int cb_gemm(void *self, int stream, const double *a, long long lda, const double *bm, long long ldb, double *c, long long ldc,
+                   int rows, int width, int n) {
+  CudaBandBackend *b = (CudaBandBackend *)self;
+  (void)ldb;
+  (void)ldc;
+  (void)n; /* the B store and the C block of the object carry their own leading dimension and width */
+  cudaEvent_t e0, e1;
+  CUDA_CHECK(cudaEventCreate(&e0));
+  CUDA_CHECK(cudaEventCreate(&e1));
+  CUDA_CHECK(cudaEventRecord(e0, b->streams[stream]));
+  const int launches = launch_local_gemm(b->s, b->backend, b->ctas, a, lda, bm, c, rows, width, b->streams[stream]);
+  CUDA_CHECK(cudaEventRecord(e1, b->streams[stream]));
+  b->g0.push_back(e0);
+  b->g1.push_back(e1);
+  return launches;
+}
+
 static void summa_run_host_banded(phpc_summa *s, int backend, int ctas, const double *hA, const double *hB, double *hC, int bands,
                                   phpc_summa_stats *stats) {
   PHPC_REQUIRE(s->size == 1, "the band pipeline is the single-rank host path");
   DeviceCtx *ctx = s->ctx;
   CUDA_CHECK(cudaSetDevice(ctx->device));
-  const size_t N = (size_t)s->N;
   const int nsteps = (int)s->steps.size();
-  const int nops = phpc_host_plan(s->m, nsteps, bands, 128, nullptr, 0);
+  const int nops = phpc::host_plan(s->m, nsteps, bands, 128, nullptr, 0);
   std::vector<phpc_host_op> ops(nops);
-  phpc_host_plan(s->m, nsteps, bands, 128, ops.data(), nops);
-  cudaStream_t streams[3] = {ctx->copy, ctx->compute, ctx->comm}; /* comm is idle on one GPU: it carries the downloads */
-  std::vector<cudaEvent_t> done(nops, nullptr);
-  std::vector<char> needed(nops, 0);
-  for (const phpc_host_op &o : ops)
-    for (int i = 0; i < o.ndeps; ++i) needed[o.deps[i]] = 1;
-  std::vector<cudaEvent_t> g0, g1;
-  int launches = 0;
+  phpc::host_plan(s->m, nsteps, bands, 128, ops.data(), nops);
+
+  CudaBandBackend cb;
+  cb.s = s;
+  cb.backend = backend;
+  cb.ctas = ctas;
+  cb.streams[0] = ctx->copy;
+  cb.streams[1] = ctx->compute;
+  cb.streams[2] = ctx->comm; /* idle on one GPU: it carries the downloads */
+  phpc::BandBackend be = {&cb, cb_copy2d, cb_record, cb_wait, cb_gemm};
+  phpc::BandGeom g;
+  g.N = s->N;
+  g.m = s->m;
+  g.n = s->n;
+  g.pi = s->pi;
+  g.pj = s->pj;
+  g.ldn = s->ldn;
+  g.steps = s->steps.data();
+  g.nsteps = nsteps;
+  g.dA = s->dA;
+  g.dB = s->dB;
+  g.dC = s->dC;
+
   CUDA_CHECK(cudaEventRecord(s->ev_begin, ctx->compute));
-  CUDA_CHECK(cudaStreamWaitEvent(streams[0], s->ev_begin, 0));
-  CUDA_CHECK(cudaStreamWaitEvent(streams[2], s->ev_begin, 0));
-  for (int i = 0; i < nops; ++i) {
-    const phpc_host_op &o = ops[i];
-    cudaStream_t st = streams[o.stream];
-    for (int d = 0; d < o.ndeps; ++d) {
-      PHPC_REQUIRE(o.deps[d] < i && done[o.deps[d]] != nullptr, "host plan dependency does not point at an earlier operation");
-      CUDA_CHECK(cudaStreamWaitEvent(st, done[o.deps[d]], 0));
-    }
-    switch (o.kind) {
-      case PHPC_HOP_UPLOAD_C:
-        CUDA_CHECK(cudaMemcpy2DAsync(s->dC + (size_t)o.row0 * s->ldn, s->ldn * sizeof(double),
-                                     hC + ((size_t)s->pi * s->m + o.row0) * N + (size_t)s->pj * s->n, N * sizeof(double),
-                                     (size_t)s->n * sizeof(double), o.rows, cudaMemcpyHostToDevice, st));
-        break;
-      case PHPC_HOP_UPLOAD_A: {
-        const phpc_summa_step &q = s->steps[o.step];
-        const size_t ld = phpc_pad_ld(q.width);
-        CUDA_CHECK(cudaMemcpy2DAsync(s->dA + q.a_off + (size_t)o.row0 * ld, ld * sizeof(double),
-                                     hA + ((size_t)s->pi * s->m + o.row0) * N + (size_t)q.k0, N * sizeof(double),
-                                     (size_t)q.width * sizeof(double), o.rows, cudaMemcpyHostToDevice, st));
-        break;
-      }
-      case PHPC_HOP_UPLOAD_B: {
-        const phpc_summa_step &q = s->steps[o.step];
-        CUDA_CHECK(cudaMemcpy2DAsync(s->dB + q.b_off, s->ldn * sizeof(double), hB + (size_t)q.k0 * N + (size_t)s->pj * s->n,
-                                     N * sizeof(double), (size_t)s->n * sizeof(double), q.width, cudaMemcpyHostToDevice, st));
-        break;
-      }
-      case PHPC_HOP_GEMM: {
-        const phpc_summa_step &q = s->steps[o.step];
-        const long long ld = phpc_pad_ld(q.width);
-        cudaEvent_t e0, e1;
-        CUDA_CHECK(cudaEventCreate(&e0));
-        CUDA_CHECK(cudaEventCreate(&e1));
-        CUDA_CHECK(cudaEventRecord(e0, st));
-        launches += launch_local_gemm(s, backend, ctas, s->dA + q.a_off + (size_t)o.row0 * ld, ld, s->dB + q.b_off,
-                                      s->dC + (size_t)o.row0 * s->ldn, o.rows, q.width, st);
-        CUDA_CHECK(cudaEventRecord(e1, st));
-        g0.push_back(e0);
-        g1.push_back(e1);
-        break;
-      }
-      case PHPC_HOP_DOWNLOAD_C:
-        CUDA_CHECK(cudaMemcpy2DAsync(hC + ((size_t)s->pi * s->m + o.row0) * N + (size_t)s->pj * s->n, N * sizeof(double),
-                                     s->dC + (size_t)o.row0 * s->ldn, s->ldn * sizeof(double), (size_t)s->n * sizeof(double), o.rows,
-                                     cudaMemcpyDeviceToHost, st));
-        break;
-      default:
-        PHPC_REQUIRE(false, "unknown host plan operation");
-    }
-    if (needed[i]) {
-      CUDA_CHECK(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-      CUDA_CHECK(cudaEventRecord(done[i], st));
-    }
-  }
+  CUDA_CHECK(cudaStreamWaitEvent(cb.streams[0], s->ev_begin, 0));
+  CUDA_CHECK(cudaStreamWaitEvent(cb.streams[2], s->ev_begin, 0));
+  const int launches = phpc::band_execute(g, ops.data(), nops, hA, hB, hC, be);
+  PHPC_REQUIRE(launches >= 0, "unknown host plan operation");
   CUDA_CHECK(cudaEventRecord(s->ev_end, ctx->compute));
-  for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaStreamSynchronize(streams[i]));
+  for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaStreamSynchronize(cb.streams[i]));
   if (stats) {
     float total = 0.f, gemm = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&total, s->ev_begin, s->ev_end));
-    for (size_t i = 0; i < g0.size(); ++i) {
+    for (size_t i = 0; i < cb.g0.size(); ++i) {
       float ms = 0.f;
-      CUDA_CHECK(cudaEventElapsedTime(&ms, g0[i], g1[i]));
+      CUDA_CHECK(cudaEventElapsedTime(&ms, cb.g0[i], cb.g1[i]));
       gemm += ms;
     }
     stats->total_ms = total;
@@ -782,10 +750,9 @@ static void summa_run_host_banded(phpc_summa *s, int backend, int ctas, const do
     stats->broadcasts = 0;
     stats->bytes_received = 0;
   }
-  for (cudaEvent_t e : done)
-    if (e) CUDA_CHECK(cudaEventDestroy(e));
-  for (cudaEvent_t e : g0) CUDA_CHECK(cudaEventDestroy(e));
-  for (cudaEvent_t e : g1) CUDA_CHECK(cudaEventDestroy(e));
+  for (cudaEvent_t e : cb.deps) CUDA_CHECK(cudaEventDestroy(e));
+  for (cudaEvent_t e : cb.g0) CUDA_CHECK(cudaEventDestroy(e));
+  for (cudaEvent_t e : cb.g1) CUDA_CHECK(cudaEventDestroy(e));
 }
 
 /* Row bands of the single-GPU host-sourced run: PHPC_HOST_BANDS, else 4 once the block is big enough
