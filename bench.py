@@ -614,10 +614,14 @@ def product_arm(args):
 
     ref_cuda = None
     if rank == 0 and world == 1 and not args.no_refcuda:
-        try:
-            ref_cuda = run_reference_cuda_build()
-        except Exception as e:  # a reported baseline must never cost the bench line
-            ref_cuda = {"unavailable": f"{type(e).__name__}: {e}"}
+        # the reference's build with (a) its default launch, one 32x32 CTA (what its own CSV sweeps use),
+        # and (b) a sane launch, 148x4 CTAs
+        ref_cuda = []
+        for n_ref, gw, gh in ((4096, 1, 1), (8192, 148, 4)):
+            try:
+                ref_cuda.append(run_reference_cuda_build(n=n_ref, gw=gw, gh=gh))
+            except Exception as e:  # a reported baseline must never cost the bench line
+                ref_cuda.append({"unavailable": f"{type(e).__name__}: {e}"})
 
     if rank == 0:
         line = {
