@@ -590,6 +590,11 @@ def product_arm(args):
         sec = measure(secondary, 1, max(1, min(2, args.steps)), False)
         other = {"value": sec["tflops"], "unit": UNIT, "ms_per_step": sec["ms"], "exposed_frac": sec["exposed"],
                  "kernels_per_step": sec["stats"].launches, "roofline": sec["roofline"]}
+    cublas = None
+    if not args.no_secondary:
+        # the strongest on-box library baseline: the same device-resident SUMMA with cuBLAS Dgemm as the local GEMM
+        cb = measure(capi.BACKEND_CUBLAS, 1, 1, False)
+        cublas = {"value": cb["tflops"], "unit": UNIT, "ms_per_step": cb["ms"], "what": "same SUMMA loop, local GEMM = cublasDgemm (library call, not the product)"}
     s.destroy()
 
     # ---------------- e2e through the reference-facing C-ABI on host matrices ----------------
@@ -644,6 +649,7 @@ def product_arm(args):
             "reference_cuda_build": ref_cuda,
             "local_gemm": names[primary],
             names[secondary]: other,
+            "cublas_dgemm": cublas,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
