@@ -3,7 +3,8 @@
  *
  * Drop-in for the reference driver (src/main.c:17-123): same five positional
  * arguments, same abort conditions and messages, same CSV file name and record.
- * Times the SUMMA with the DMMA kernel, then the same SUMMA with cuBLAS Dgemm.
+ * Times the SUMMA with the library's default local GEMM (the tcgen05 kernel; PHPC_GEMM=dmma selects native FP64), then
+ * the same SUMMA with cuBLAS Dgemm.
  *
  * Deliberate differences:
  *   - C is zeroed before each pass (the reference accumulates the cuBLAS pass on
@@ -131,7 +132,7 @@ int main(int argc, char *argv[]) {
 
     MPI_Barrier(MPI_COMM_WORLD);
     start_time = get_cur_time();
-    phpc_summa_run(s, PHPC_BACKEND_DMMA, grid_width * grid_height, NULL, &st);
+    phpc_summa_run(s, phpc_default_backend(), grid_width * grid_height, NULL, &st);
     MPI_Barrier(MPI_COMM_WORLD);
     cuda_time = get_cur_time() - start_time;
     cuda_gpu_time = st.gemm_ms / 1000.f;

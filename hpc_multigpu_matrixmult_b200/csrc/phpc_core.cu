@@ -555,6 +555,8 @@ bool phpc_use_ozaki(void) {
   const char *g = getenv("PHPC_GEMM");
   return !(g && !strcmp(g, "dmma"));
 }
+/* the same choice for C callers of the object API (main.out in device mode): PHPC_BACKEND_OZAKI (2) or PHPC_BACKEND_DMMA (0) */
+extern "C" int phpc_default_backend(void) { return phpc_use_ozaki() ? 2 : 0; }
 
 static void launch_dmma_adapter(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC,
                                 long long ldc, int m, int k, int n, int ctas, cudaStream_t s) {

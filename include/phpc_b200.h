@@ -91,6 +91,10 @@ void phpc_fill_device(double *d, long long ld, long long rows, long long cols, l
 void phpc_fill_host(double *h, long long ld, long long rows, long long cols, long long row0, long long col0, long long N, int kind,
                     unsigned long long seed);
 
+/* The local GEMM the reference-named entry points (phpc_gemm_cuda, phpc_gemm_summa_cuda) run in this process, as a backend
+ * number for phpc_summa_run: PHPC_BACKEND_OZAKI (tcgen05, default) or PHPC_BACKEND_DMMA (environment PHPC_GEMM=dmma). */
+int phpc_default_backend(void);
+
 /* The configuration the tcgen05 (Ozaki) path of this process runs with (environment PHPC_OZAKI_DIGITS / PHPC_OZAKI_KERNEL /
  * PHPC_OZAKI_SLICES, else the built-in defaults): digits per operand, int8 digit products per FP64 product
  * (digits*(digits+1)/2), kernel 0 = 1-CTA, 1 = 2-CTA (relay), 2 = 2-CTA (tensor-map loads), balanced = 1 for balanced
