@@ -5,7 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#define PHPC_B200_VERSION 100
+#define PHPC_B200_VERSION 101 /* 101: phpc_host_plan, phpc_default_backend, phpc_ozaki_config, bring-up diagnostics */
 
 #define PHPC_MAX_DEVICES 16
 
