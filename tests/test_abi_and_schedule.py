@@ -130,3 +130,22 @@ def test_csv_runner_reads_the_reference_config_format(built, tmp_path):
     b200 = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "run_tests_csv.py"),
                            os.path.join(ROOT, "tests", "configs", "b200_configs.csv"), "--dry-run"], capture_output=True, text=True, timeout=60)
     assert b200.returncode == 0 and len(b200.stdout.strip().splitlines()) == 10
+
+
+def test_ozaki_config_follows_the_environment(capi, monkeypatch):
+    """phpc_ozaki_config / phpc_default_backend: one place decides what the tcgen05 path runs with (environment, else the
+    built-in defaults = the kernel that was validated on hardware in round 1)."""
+    for k in ("PHPC_OZAKI_DIGITS", "PHPC_OZAKI_KERNEL", "PHPC_OZAKI_SLICES", "PHPC_GEMM"):
+        monkeypatch.delenv(k, raising=False)
+    lib = capi.load()
+    assert capi.ozaki_config() == {"digits": 8, "products": 36, "kernel": "1cta", "balanced": False}
+    assert lib.phpc_default_backend() == capi.BACKEND_OZAKI
+    monkeypatch.setenv("PHPC_OZAKI_DIGITS", "balanced")
+    monkeypatch.setenv("PHPC_OZAKI_KERNEL", "2cta-tma")
+    assert capi.ozaki_config() == {"digits": 7, "products": 28, "kernel": "2cta-tma", "balanced": True}
+    monkeypatch.setenv("PHPC_OZAKI_DIGITS", "trunc")
+    monkeypatch.setenv("PHPC_OZAKI_KERNEL", "2cta")
+    monkeypatch.setenv("PHPC_OZAKI_SLICES", "6")
+    assert capi.ozaki_config() == {"digits": 6, "products": 21, "kernel": "2cta", "balanced": False}
+    monkeypatch.setenv("PHPC_GEMM", "dmma")
+    assert lib.phpc_default_backend() == capi.BACKEND_DMMA
