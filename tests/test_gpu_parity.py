@@ -160,15 +160,25 @@ def _device_gemm(capi, lib, n, kind, scale=1.0, cublas=False):
     return dA, dB, dC
 
 
-def test_full_size_n16384_properties(gpu, capi, oracle):
-    """BASELINE config 2 (N=16384, one GPU): size-independent properties instead of a CPU GEMM.
+@pytest.mark.parametrize("kernel", ["tcgen05", "dmma"])
+def test_full_size_n16384_properties(gpu, capi, oracle, kernel):
+    """BASELINE config 2 (N=16384, one GPU) on BOTH kernels — the tcgen05 (Ozaki) default of the entry points, whose
+    launcher cuts K = 16384 into two chunks, and the native-FP64 DMMA kernel: size-independent properties instead of
+    a CPU GEMM.
     (a) 256 sampled elements against correctly rounded dot products of regenerated rows/columns;
-    (b) against cuBLAS Dgemm on the same device inputs (rel Frobenius on a 2048x2048 window);
+    (b) against cuBLAS Dgemm on the same device inputs (rel Frobenius on a 512x2048 window);
     (c) linearity: running the GEMM twice into the same C doubles it (C += semantics)."""
     lib = gpu
     n = 16384
     dA, dB, dC = _device_gemm(capi, lib, n, capi.FILL_SEEDED)
-    assert lib.phpc_gemm_device(dA, n, dB, n, dC, n, n, n, n, 0, None) == 1
+
+    def gemm():
+        if kernel == "tcgen05":
+            assert lib.phpc_gemm_device_ozaki(dA, n, dB, n, dC, n, n, n, n, 0, None) >= 2  # at least two K chunks
+        else:
+            assert lib.phpc_gemm_device(dA, n, dB, n, dC, n, n, n, n, 0, None) == 1
+
+    gemm()
     lib.phpc_device_synchronize()
 
     def window(ptr, r0, c0, rows, cols):
@@ -195,14 +205,31 @@ def test_full_size_n16384_properties(gpu, capi, oracle):
     w1 = window(dC, 4096, 8192, 512, 2048)
     w2 = window(dC2, 4096, 8192, 512, 2048)
     assert oracle.rel_frobenius(w1, w2) <= 1e-14
-    # (c) C += : second pass doubles every element exactly (x + x is exact in binary FP)
-    lib.phpc_gemm_device(dA, n, dB, n, dC, n, n, n, n, 0, None)
+    # (c) C += : second pass doubles every element up to one rounding per K chunk (x + x itself is exact)
+    gemm()
     lib.phpc_device_synchronize()
     w3 = window(dC, 4096, 8192, 512, 2048)
     assert oracle.rel_frobenius(w3, 2 * w1) <= 1e-15
     for p in (dA, dB, dC, dC2):
         lib.phpc_device_free(p)
-    print(f"N=16384 sampled-dot worst error / bound = {worst:.3f}")
+    print(f"N=16384 [{kernel}] sampled-dot worst error / bound = {worst:.3f}")
+
+
+@pytest.mark.parametrize("m,k,n", [(260, 20000, 140), (128, 32768, 130), (140, 16385, 257)])
+def test_ozaki_multi_k_chunk_launcher_vs_oracle(gpu, capi, oracle, m, k, n):
+    """K larger than one int32-exact chunk: the launcher of the tcgen05 kernel walks several K chunks (exponents, digit
+    split and MMA kernel per chunk, C += per chunk).  k = 32768 is the shape of the headline 1x1 run; 16385 leaves a
+    chunk of a single column.  Against the oracle (reference summation order) and correctly rounded dot products."""
+    a = oracle.fill(m, k, kind=1, seed=111)
+    b = oracle.fill(k, n, kind=1, seed=222)
+    c0 = oracle.fill(m, n, kind=1, seed=333)
+    c, launched = _device_gemm_from_numpy(capi, gpu, a, b, c0, "ozaki")
+    assert launched >= 12  # at least two chunks
+    _check(oracle, c, oracle.gemm_block(a, b, c0), a, b)
+    rng = np.random.default_rng(k)
+    for i, j in zip(rng.integers(0, m, 24), rng.integers(0, n, 24)):
+        exact = oracle.dot_exact(a[i], np.ascontiguousarray(b[:, j])) + c0[i, j]
+        assert abs(c[i, j] - exact) <= 4.0 * np.sqrt(k) * U * float(np.abs(a[i]) @ np.abs(b[:, j]))
 
 
 def test_index_fill_large_n_against_closed_form(gpu, capi, oracle):
