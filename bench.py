@@ -276,6 +276,52 @@ def measured_peaks():
         return None
 
 
+def sampled_check(capi, L, N, pairs, got, passes):
+    """Self-verification of a bench result: `got[(i, j)]` = C[i][j] after `passes` accumulations of A*B, for global element
+    positions `pairs`.  Rows of A / columns of B are regenerated on the host from the counter-based fill the device blocks
+    were generated with (the library's own phpc_fill_host: same splitmix64 stream), the dot product is summed exactly
+    (math.fsum over FP64 products), and the bound is the one the parity tests use: 4*sqrt(N)*2^-53 * sum|a||b| per pass.
+    Returns (ok, worst error / bound)."""
+    import math
+
+    import numpy as np
+
+    dp = capi.c_double_p
+    rows = sorted({i for i, _ in pairs})
+    cols = sorted({j for _, j in pairs})
+    a = {}
+    for i in rows:
+        v = np.empty(N)
+        L.phpc_fill_host(v.ctypes.data_as(dp), N, 1, N, int(i), 0, N, capi.FILL_SEEDED, capi.SEED_A)
+        a[i] = v
+    b = {}
+    for j in cols:
+        v = np.empty(N)
+        L.phpc_fill_host(v.ctypes.data_as(dp), 1, N, 1, 0, int(j), N, capi.FILL_SEEDED, capi.SEED_B)
+        b[j] = v
+    worst = 0.0
+    for (i, j) in pairs:
+        prod = a[i] * b[j]
+        want = passes * math.fsum(prod)
+        bound = passes * 4.0 * math.sqrt(N) * 2.0 ** -53 * float(np.abs(prod).sum())
+        err = abs(float(got[(i, j)]) - want)
+        if not err <= bound:  # also catches NaN
+            return False, float("inf")
+        worst = max(worst, err / bound)
+    return True, worst
+
+
+def sample_positions(row0, rows, col0, cols, seed, count=8):
+    """count x count element positions of the block [row0, row0+rows) x [col0, col0+cols): first and last row / column
+    (first and last tile, band and chunk edges) plus seeded random ones."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    ri = sorted({row0, row0 + rows - 1, *(int(x) for x in rng.integers(row0, row0 + rows, count - 2))})
+    ci = sorted({col0, col0 + cols - 1, *(int(x) for x in rng.integers(col0, col0 + cols, count - 2))})
+    return [(i, j) for i in ri for j in ci]
+
+
 def host_matrices(capi, N, dims, coords, pin=True):
     """FULL N x N host A, B, C as the reference API wants them; only the windows this rank
     owns are filled and page-locked (the rest of the address range is never touched)."""
@@ -360,28 +406,33 @@ def e2e_measure(args, capi, L, comm, dims, rank, world, barrier, max_over_ranks)
         return sum(ts) / len(ts), e2e_steps + 1
 
     def verified(passes):
-        if world != 1:  # other grids hold only their own windows of A and B on the host
-            return None
-        rng = np.random.default_rng(2026)
-        rows = np.concatenate([[0, N - 1], rng.integers(0, N, 14)])  # first/last row: first and last band
-        cols = np.concatenate([[0, N - 1], rng.integers(0, N, 14)])
-        for i in rows:
-            for j in cols:
-                want = passes * float(A[i, :] @ B[:, j])
-                scale = passes * float(np.abs(A[i, :]) @ np.abs(B[:, j]))
-                if not abs(C[i, j] - want) <= 1e-12 * scale:
-                    return False
-        return True
+        """Rank 0 holds the full gathered C: sampled elements of EVERY rank's block (so the gather is checked too); the other
+        ranks check their own block, which the entry point leaves at its global offset in their C (reference :44)."""
+        pairs = []
+        if rank == 0:
+            for bi in range(dims[0]):
+                for bj in range(dims[1]):
+                    pairs += sample_positions(bi * m_blk, m_blk, bj * n_blk, n_blk, 2026 + bi * 16 + bj, 5 if world > 1 else 8)
+        else:
+            pairs = sample_positions(pi * m_blk, m_blk, pj * n_blk, n_blk, 2026 + rank, 5)
+        ok, worst = sampled_check(capi, L, N, pairs, {(i, j): C[i, j] for (i, j) in pairs}, passes)
+        return ok, worst, len(pairs)
 
     secs, passes = leg()
-    ok = verified(passes)
+    ok, worst, nsamples = verified(passes)
+    ok = max_over_ranks(0.0 if ok else 1.0) == 0.0  # every rank's check must pass
+    worst = max_over_ranks(worst)
     secs = max_over_ranks(secs)
     for ptr, _ in regs:
         L.phpc_host_unregister(ptr)
     L.phpc_summa_release_cache()
     bands = os.environ.get("PHPC_HOST_BANDS", "4 (default for blocks of >= 8192 rows)") if world == 1 else "n/a"
     return {"value": flops / secs / 1e12 if ok is not False else None, "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * N * N,
-            "d2h_bytes_per_step": 8 * N * N, "ms_per_step": secs * 1e3, "steps": e2e_steps, "verified": ok, "host_row_bands": bands,
+            "d2h_bytes_per_step": 8 * N * N, "ms_per_step": secs * 1e3, "steps": e2e_steps, "verified": ok,
+            "verify": {"elements_checked_rank0": nsamples, "worst_error_over_bound": worst, "passes_accumulated": passes,
+                       "how": "sampled C elements of every rank's block in rank 0's gathered host C (and each rank's own block) vs exactly summed FP64 "
+                              "dot products of regenerated rows/columns; bound 4*sqrt(N)*2^-53*sum|a||b| per pass"},
+            "host_row_bands": bands,
             "api": "phpc_gemm_summa_cuda(grid_comm, A, B, C, N, ...) on page-locked full N x N host matrices; owned blocks H2D, C block "
                    "H2D and D2H + gather to rank 0 inside the timed region (one GPU: C row bands pipelined under the GEMMs)"}
 
@@ -488,14 +539,17 @@ def product_arm(args):
     s.fill(capi.FILL_SEEDED)
     stream = torch.cuda.current_stream()
     sptr = ctypes.c_void_p(stream.cuda_stream)
-    oz = capi.ozaki_config()  # what the library's tcgen05 path runs with in this process (environment, else its defaults)
-    slices, pairs, balanced, two_cta = oz["digits"], oz["products"], oz["balanced"], oz["kernel"] != "1cta"
-    oz_kernel = (f"phpc::oz::ozaki_gemm_2cta_kernel<{slices}> [{oz['kernel']}] (tcgen05.mma.cta_group::2 kind::i8, M=256 per CTA pair" if two_cta
-                 else f"phpc::oz::ozaki_gemm_kernel<{slices}> (tcgen05.mma kind::i8") + ", int32 accumulators in TMEM, cp.async.bulk ring)"
+    oz = capi.ozaki_config()  # the fixed arithmetic of the library's tcgen05 path
+    slices, pairs = oz["digits"], oz["products"]
+    oz_kernel = ("phpc::oz::ozaki_gemm_kernel (tcgen05.mma.cta_group::1.kind::i8 M=128, N=256 over adjacent digit pairs, int32 accumulators in all 512 "
+                 "TMEM columns, cp.async.bulk mbarrier ring, warp-specialised, wave-synchronised tile starts)")
     fp64_pk, fp64_src = fp64_peak()
     int8_pk, int8_src = int8_peak()
 
+    passes_on_c = [0]  # C += A*B passes accumulated in the device C blocks since s.fill() zeroed them
+
     def measure(backend, warmup, steps, sample_clocks):
+        passes_on_c[0] += warmup + steps
         for _ in range(warmup):
             s.run(backend, 0, sptr, stats=False)
         torch.cuda.synchronize()
@@ -526,12 +580,10 @@ def product_arm(args):
                     "traffic": None, "kernel": oz_kernel,
                     "ops_per_launch": 2.0 * m_blk * n_blk * k_per_gemm * pairs, "kernel_ms": gemm_ms, "fp64_equivalent_tflops": gemm_tflops,
                     "fp64_equivalent_vs_fp64_peak": gemm_tflops / fp64_pk, "peak_source": int8_src,
-                    "note": f"{pairs} int8 MMAs per FP64 MMA ({slices} {'balanced base-256' if balanced else 'truncated 7-bit'} digits); kernel_ms spans the whole local GEMM (exponent + split kernels "
-                            "included, < 3 % at this size)",
-                    "traffic_note": "no ncu --set full capture of this launch shape yet; the N=8192 launch of the same kernel family read 11.5 GB "
-                                    "and wrote 1.1 GB of DRAM (algorithmic: 1.07 GB of digits + 2 passes x 1.07 GB of C) = 8.5 % of HBM peak, "
-                                    "profiles/ncu_ozaki_gemm_n8192_r01_v3.txt"}
-            k_launch = min(int(k_per_gemm), int(os.environ.get("PHPC_OZ_KC", "8192")))  # the launcher cuts K into chunks of this size
+                    "note": f"{pairs} int8 MMAs per FP64 MMA ({slices} balanced base-256 digits); kernel_ms spans the whole local GEMM (exponent, guard and split "
+                            "kernels included, < 3 % at this size)",
+                    "traffic_note": "no ncu capture of this launch shape committed under profiles/ozaki_traffic*.json"}
+            k_launch = min(int(k_per_gemm), oz["k_chunk"])  # the launcher cuts K into chunks of this size
             tr = ozaki_traffic(m_blk, k_launch, n_blk)
             if tr:
                 roof["traffic"] = tr[0]
@@ -581,6 +633,26 @@ def product_arm(args):
             prim["clocks"]["remeasured_after"] = first_clocks
     value, ms_per_step, clocks, st = prim["tflops"], prim["ms"], prim["clocks"], prim["stats"]
     exposed_frac = prim["exposed"]
+
+    # ---------------- self-verification of `value`: every rank checks sampled elements of ITS C block ----------------
+    # (the device blocks hold passes x A*B after the warm-up and timed steps; the driver's pytest box has one GPU, so this is
+    # the multi-GPU parity check that runs with every bench line)
+    m_blk, n_blk = s.block
+    pi, pj = s.coords
+    pairs = sample_positions(pi * m_blk, m_blk, pj * n_blk, n_blk, 4242 + rank, 8)
+    got = {}
+    for i in sorted({i for i, _ in pairs}):
+        row = s.read_c_block(i - pi * m_blk, 0, 1, n_blk)[0]
+        for (i2, j) in pairs:
+            if i2 == i:
+                got[(i, j)] = row[j - pj * n_blk]
+    v_ok, v_worst = sampled_check(capi, L, N, pairs, got, passes_on_c[0])
+    value_verified = max_over_ranks(0.0 if v_ok else 1.0) == 0.0
+    value_verify = {"elements_checked_per_rank": len(pairs), "ranks": world, "worst_error_over_bound": max_over_ranks(v_worst),
+                    "passes_accumulated": passes_on_c[0],
+                    "how": "after the timed steps every rank reads sampled elements of its device C block (first/last row and column of the block + "
+                           "random ones) and compares them with passes x the exactly summed FP64 dot product of the regenerated row of A and "
+                           "column of B; bound 4*sqrt(N)*2^-53*sum|a||b| per pass (the parity tests' bound)"}
     launches_per_step = st.launches
     bytes_rx = st.bytes_received
     steps_per_summa = st.steps
@@ -635,14 +707,19 @@ def product_arm(args):
             "data": "synthetic",
             "config": {"workload": f"SUMMA C+=A*B, N={N}, FP64 in/out, splitmix64-seeded uniform(-1,1) A/B generated in HBM, owned blocks device-resident",
                        "local_gemm": names[primary],
-                       "arithmetic": (f"FP64 rebuilt exactly from {slices} signed {'8-bit balanced' if balanced else '7-bit'} digits per operand: "
-                                      "s8 x s8 -> s32 on tcgen05, FP64 recombination (rel. Frobenius difference to native FP64 1.5e-15)")
+                       "arithmetic": (f"emulated FP64: rebuilt from {slices} balanced base-256 digits per operand (54 bits below each row / column maximum "
+                                      f"of a K chunk of {oz['k_chunk']}), {pairs} s8 x s8 -> s32 products on tcgen05, exact FP64 recombination; normwise error "
+                                      "model (rel. Frobenius difference to native FP64 ~1e-15); chunks with Inf/NaN, near-range exponents or > 2^40 "
+                                      "spread inside a row / column run on the native-FP64 DMMA kernel")
                        if primary == capi.BACKEND_OZAKI else "native FP64 DMMA",
                        "N": N, "process_grid": f"{dims[0]}x{dims[1]}", "k_chunk": kc_used, "summa_steps": steps_per_summa,
                        "cache": "inputs_larger_than_l2 (operands are GiBs; L2 is 126 MB)", "exposed_broadcast_frac": exposed_frac,
                        "nvlink_bytes_received_rank0_per_step": bytes_rx},
+            "value_verified": value_verified,
+            "value_verify": value_verify,
             "clocks": clocks,
             "e2e": e2e,
+            "e2e_steps_averaged": (e2e or {}).get("steps"),
             "gpu_launches": launches_per_step * args.steps,
             "roofline": prim["roofline"],
             "cpu_baseline": cpu,

@@ -126,8 +126,10 @@ def load():
     dev_gemm = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong] + [ctypes.c_int] * 3
     L.phpc_gemm_device.argtypes = dev_gemm + [ctypes.c_int, ctypes.c_void_p]
     L.phpc_gemm_device.restype = ctypes.c_int
-    L.phpc_gemm_device_ozaki.argtypes = dev_gemm + [ctypes.c_int, ctypes.c_void_p]
+    L.phpc_gemm_device_ozaki.argtypes = dev_gemm + [ctypes.c_void_p]
     L.phpc_gemm_device_ozaki.restype = ctypes.c_int
+    L.phpc_ozaki_fallback_chunks.restype = ctypes.c_longlong
+    L.phpc_default_backend.restype = ctypes.c_int
     L.phpc_gemm_device_cublas.argtypes = dev_gemm + [ctypes.c_void_p]
     L.phpc_gemm_device_cublas.restype = None
     L.phpc_gemm_device_timed.argtypes = dev_gemm + [ctypes.c_int, ctypes.c_int, ctypes.c_int]
@@ -254,10 +256,15 @@ def summa_schedule(N, r, c, pi, pj, kc=0):
 
 
 def ozaki_config():
-    """What the tcgen05 (Ozaki) path of this process runs with: environment, else the library's defaults."""
+    """The fixed arithmetic of the tcgen05 (Ozaki) path: digits per operand, int8 products per FP64 product, K chunk, guard spread."""
     v = [ctypes.c_int() for _ in range(4)]
     load().phpc_ozaki_config(*[ctypes.byref(x) for x in v])
-    return {"digits": v[0].value, "products": v[1].value, "kernel": ("1cta", "2cta", "2cta-tma")[v[2].value], "balanced": bool(v[3].value)}
+    return {"digits": v[0].value, "products": v[1].value, "k_chunk": v[2].value, "max_spread": v[3].value}
+
+
+def default_backend():
+    """The local GEMM the reference-named entry points run in this process (tcgen05 unless PHPC_GEMM=dmma)."""
+    return load().phpc_default_backend()
 
 
 def host_plan(m, nsteps, bands, align=128):
@@ -323,7 +330,8 @@ class Summa:
     def zero_c(self):
         self.L.phpc_summa_zero_c(self.h)
 
-    def run(self, backend=BACKEND_DMMA, ctas=0, stream=None, stats=True):
+    def run(self, backend=None, ctas=0, stream=None, stats=True):
+        backend = default_backend() if backend is None else backend
         st = SummaStats() if stats else None
         self.L.phpc_summa_run(self.h, backend, ctas, stream, ctypes.byref(st) if stats else None)
         return st
@@ -334,7 +342,8 @@ class Summa:
         k = self.L.phpc_summa_timeline(self.h, a, b, n)
         return [(a[i], b[i]) for i in range(k)]
 
-    def run_host(self, A, B, C, backend=BACKEND_DMMA, ctas=0, gather=True):
+    def run_host(self, A, B, C, backend=None, ctas=0, gather=True):
+        backend = default_backend() if backend is None else backend
         st = SummaStats()
         self.L.phpc_summa_run_host(self.h, backend, ctas, _dp(A), _dp(B), _dp(C), 1 if gather else 0, ctypes.byref(st))
         return st

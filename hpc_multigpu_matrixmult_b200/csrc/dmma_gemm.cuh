@@ -59,6 +59,7 @@ struct GemmParams {
   int M, N, K;
   int tiles_m, tiles_n, k_iters;
   unsigned int *sched; /* [0] next tile, [1] CTAs finished (self-resetting) */
+  const int *guard;    /* fallback launches of the tcgen05 path (phpc_launch_ozaki): run only when *guard != 0; NULL = always run */
 };
 
 /* ---- thin PTX wrappers ------------------------------------------------- */
@@ -115,6 +116,7 @@ __device__ __forceinline__ void tile_coords(int idx, int tiles_m, int tiles_n, i
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     dmma_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  if (p.guard && *p.guard == 0) return; /* uniform over the grid, before the tile counter is touched */
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u; /* 128B swizzle atoms are 1 KiB */
   const uint32_t bars = smem_base + STAGES * STAGE_BYTES;           /* full[STAGES], empty[STAGES], tile[STAGES] */

@@ -2,38 +2,57 @@
  * ozaki_gemm.cuh — FP64 GEMM on the 5th-generation tensor cores (tcgen05 + TMEM).
  *
  * tcgen05.mma has no FP64 kind, so the FP64 product is rebuilt EXACTLY from integer products (the
- * Ozaki scheme): every row of A and every column of B is scaled by a power of two and cut into S
- * signed 7-bit digits (ozaki_split.cuh),
- *     a_ik = 2^eA[i] * sum_t A_t[i][k] * 2^(-7t),   b_kj = 2^eB[j] * sum_u B_u[k][j] * 2^(-7u),
+ * Ozaki scheme): every row of A and every column of B of a K chunk is scaled by a power of two,
+ * rounded to BAL_BITS = 54 bits below its row / column maximum and written in base 256 with
+ * BALANCED digits in [-128, 127] (ozaki_split.cuh),
+ *     a_ik = 2^(eA[i]-54) * sum_{t=1..7} A_t[i][k] * 256^(7-t),   b_kj likewise with eB[j], B_u,
  * the digit matrices are multiplied on the int8 tensor pipe with exact int32 accumulation in TMEM
- * (|A_t.B_u| <= K * 127^2, no rounding at all), and
- *     C[i][j] += 2^(eA[i]+eB[j]) * sum_g 2^(-7g) * P_g[i][j],   P_g = sum_{t+u=g} A_t.B_u
- * is applied in FP64 by the epilogue warps.  Groups with g > S+1 are dropped (their weight is below
- * 2^(-7(S+1)) of the row/column scale), so S(S+1)/2 int8 MMAs stand for one FP64 MMA; S = 8 carries
- * 56 bits.  The reference kernel this replaces is gemm_kernel of src/phpc_gemm.cu:6-57 (same
- * C += A.B contract); the arithmetic differs from it only in the order of exact partial sums.
+ * (|sum over K <= 8192 of up to 7 products| < 2^31, no rounding at all), and
+ *     C[i][j] += 2^(eA[i]+eB[j]-108) * sum_g 256^(14-g) * P_g[i][j],   P_g = sum_{t+u=g} A_t.B_u
+ * is applied in FP64 by the epilogue warps.  Groups g > 8 are dropped: their weight is below 2^-56 of
+ * the row/column scale and balanced digits keep their sign, so what is dropped still cancels.
+ * 28 int8 MMAs stand for one FP64 MMA.  The reference kernel this replaces is gemm_kernel of
+ * src/phpc_gemm.cu:6-57 (same C += A.B contract); the arithmetic differs from it only in the
+ * order of exact partial sums and in the two FP64 additions per K chunk.
  *
  * Kernel (one CTA per SM, persistent over 128 x 128 output tiles, static round robin):
  *   K-outer schedule  per 32-byte k step ALL needed digit tiles of A and B are staged once (one
  *               4 KiB slot per digit matrix) and every pair (t,u) of up to four groups is issued from
  *               them, one TMEM accumulator (128 columns) per group = all 512 TMEM columns:
- *                 pass 1  groups S+1 .. S-2  (the 4 least significant; needs every digit)
- *                 pass 2  groups S-3 .. 2    (digits 1..S-4 only; two k steps per stage)
+ *                 pass 1  groups 8 .. 5  (22 digit products, needs every digit)
+ *                 pass 2  groups 4 .. 2  (6 digit products, digits 1..3 only; two k steps per stage)
+ *   paired MMAs       digits u and u+1 of B lie back to back in a stage, and 8-row groups are 256 B apart
+ *               in the canonical layout, so ONE tcgen05.mma with N = 256 multiplies A_t by
+ *               [B_u | B_u+1] into the ADJACENT accumulators of groups t+u and t+u+1: 16 instructions
+ *               instead of 28 per k step and A is read from shared memory once per two digit
+ *               products (96 instead of 128 B/clk of shared-memory reads: room for the bulk copies
+ *               that refill the ring; measured +8 % and -38 % DRAM traffic, profiles/ozaki_knobs_r02.jsonl)
  *   digit stores  written by the split kernels ALREADY in the shared-memory order the tensor core
  *               wants (UMMA canonical K-major, no swizzle: 8-row x 16-byte core matrices; a 128-row x
  *               32-byte tile = 4 KiB, k chunks 128 B apart, 8-row groups 256 B apart), tile after tile:
  *               store[row tile][k step][digit][4 KiB], so a k step of a pass is ONE contiguous global
  *               range per operand.
+ *   wave start  the CTAs working on tiles i*grid .. (i+1)*grid-1 (16 tile rows x ~9 tile columns) share
+ *               A row panels and B column panels, which only hit in L2 if they are streamed at the same
+ *               time.  Free-running CTAs drift apart by more than a tile (measured 470-580 us after 110
+ *               tiles of 416 us) and the panels are then fetched from DRAM again and again (623 GB for a
+ *               32768 x 8192 x 32768 launch).  The producers therefore start every tile together: one
+ *               atomic counter per wave (all CTAs are resident: grid <= SM count, one CTA per SM).
  *   warp 0      producer: two cp.async.bulk copies per k step into a 3-stage mbarrier ring
- *   warp 1      TMEM allocator + MMA issuer: the whole warp walks warp-uniform, fully unrolled loops
- *               and one elected lane issues tcgen05.mma.kind::i8 128x128x32 / tcgen05.commit (with the
- *               loops inside `if (lane == 0)` every MMA cost 140-180 cycles of register -> uniform
- *               register moves instead of 65; tools/umma_rate.cu, profiles/umma_rate*_r01.jsonl)
- *   warps 2-5   epilogue: tcgen05.ld the four int32 accumulators of a pass, combine them exactly in
- *               FP64 (<= 52 significant bits), transpose through shared memory, one coalesced
+ *   warp 1      TMEM allocator + MMA issuer: the whole warp walks warp-uniform, fully unrolled code
+ *               and one elected lane issues tcgen05.mma.kind::i8 / tcgen05.commit (with the loops inside
+ *               `if (lane == 0)` every MMA cost 140-180 cycles of register -> uniform register moves
+ *               instead of 65; tools/umma_rate.cu, profiles/umma_rate*_r01.jsonl)
+ *   warps 2-5   epilogue: tcgen05.ld the int32 accumulators of a pass, combine them exactly in
+ *               FP64 (<= 53 significant bits), transpose through shared memory, one coalesced
  *               read-modify-write of C per pass with 32 loads in flight per lane
- * Earlier variants (pair-outer 128x256 tiles with TMA; K-outer with 16 TMA boxes per step) and what
- * ncu said about them are in profiles/ozaki_experiments_r01.md.
+ *   guard       *p.guard != 0 (set by the exponent kernels: non-finite input, exponents near the FP64
+ *               range limits, rows/columns spanning more than MAX_SPREAD binary orders of magnitude)
+ *               makes the kernel return at once; the native-FP64 DMMA kernel launched right after it
+ *               with the opposite predicate computes that K chunk instead (phpc_launch_ozaki).
+ * Earlier variants (pair-outer 128x256 tiles with TMA; K-outer with 16 TMA boxes per step; truncated
+ * 7-bit digits, 36 products; a 2-CTA cta_group::2 kernel) and what was measured on them are in
+ * profiles/ozaki_experiments_r01.md, profiles/ozaki_variants_r02.jsonl and profiles/ozaki_knobs_r02.jsonl.
  */
 #pragma once
 #include <cuda.h>
@@ -45,44 +64,46 @@
 namespace phpc {
 namespace oz {
 
-constexpr int DIGIT_BITS = 7;
-/* EXPERIMENTAL (PHPC_OZAKI_DIGITS=balanced, not validated on hardware in round 1): balanced base-256
- * digits in [-128,127] of the value rounded to BAL_BITS bits below its row/column scale; 7 digits,
- * 28 digit products, same accuracy in the integer model (oracle/ozaki_model.py, gemm_balanced). */
-constexpr int BAL_BITS = 54;
-constexpr int MAX_SLICES = 8;
+constexpr int S = 7;          /* digits per operand */
+constexpr int DIGIT_BITS = 8; /* balanced base-256 digits */
+constexpr int BAL_BITS = 54;  /* bits kept below the row / column scale */
+constexpr int PRODUCTS = S * (S + 1) / 2;
+constexpr int KC_MAX = 8192;  /* K chunk: 7 products x 8192 x 128^2 < 2^31 (exact up to K = 18724) */
 constexpr int ZERO_EXP = -2147483647 - 1; /* exponent of an all-zero row / column */
-constexpr int NONFINITE_EXP = 2147483647; /* the row / column holds an Inf or NaN: its C elements become NaN */
+constexpr int NONFINITE_EXP = 2147483647; /* the row / column holds an Inf or NaN (the guard sends the chunk to the DMMA kernel) */
+constexpr int MAX_SPREAD = 40; /* guard: nonzero entries of one row / column of a K chunk may span at most 2^40 (every entry keeps >= 16 bits) */
+constexpr int EXP_SUM_MIN = -960, EXP_SUM_MAX = 960; /* guard: eA[i] + eB[j] stays where 2^(eA+eB-108+..) and its product are normal numbers */
 
 constexpr int BM = 128;
 constexpr int BN = 128;
 constexpr int BKB = 32;                /* bytes of k per step = one int8 MMA (K = 32) */
 constexpr int SLOT_BYTES = BM * BKB;   /* one digit tile: 128 rows x 32 B */
 constexpr int TILE_BYTES = SLOT_BYTES;
-constexpr int MAX_S = MAX_SLICES;
-constexpr int STAGE_BYTES = 2 * MAX_S * SLOT_BYTES; /* A digit slots then B digit slots */
+constexpr int STAGE_BYTES = 2 * S * SLOT_BYTES; /* A digit slots then B digit slots: 56 KiB */
 constexpr int STAGES = 3;
 constexpr int THREADS = 192;           /* warp 0 producer, warp 1 MMA, warps 2-5 epilogue */
 constexpr int EPI_WARP_BYTES = 32 * 33 * 8; /* per epilogue warp: 32 x 32 doubles, padded */
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * EPI_WARP_BYTES;
 constexpr int GROUPS_PER_PASS = 4;
+constexpr int NPASS = 2;
 constexpr int TMEM_COLS = GROUPS_PER_PASS * BN; /* 512 */
+static_assert(SMEM_BYTES <= 232448, "dynamic shared memory per CTA");
 
 struct Params {
   double *C;
   long long ldc;
   int M, N;
   int ksteps; /* padded K / 32 */
-  int S;      /* digits per operand */
   const int *eA;
   const int *eB;
   int tiles_m, tiles_n;
   const int8_t *TA; /* [tiles_m][ksteps][S][4096] */
   const int8_t *TB; /* [tiles_n][ksteps][S][4096] */
-  int prefetch;     /* k steps of L2 prefetch ahead of the shared-memory ring (0 = off) */
-  int flags;        /* diagnostics: 1 = epilogue skips the C read-modify-write, 2 = no operand loads (MMA rate only) */
-  unsigned int *progress; /* bring-up aid of the experimental 2-CTA kernel (PHPC_OZ_PROGRESS=1): host-mapped words, 8 per CTA,
-                           * where every warp role records how far it got, readable from the host WHILE a kernel hangs */
+  const int *guard;        /* != 0: this K chunk belongs to the native-FP64 kernel, return at once */
+  unsigned int *wave_sync; /* one zeroed counter per wave of gridDim.x tiles */
+  int flags;               /* diagnostics (tools/ozaki_knobs.py): 1 = epilogue skips the C read-modify-write, 2 = no operand loads,
+                            * 4 = no wave synchronisation */
+  unsigned long long *tstamp; /* diagnostics: globaltimer at the start of every tile's loads [2*tile] and end of its epilogue [2*tile+1] */
 };
 
 /* instruction descriptor: s8 x s8 -> s32, A and B K-major */
@@ -132,11 +153,8 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, int (&v)[32])
       : "memory");
 }
 
-/* 2^e as a double (e clamped to the normal range; INT_MIN exponents mean "all zero") */
-__device__ __forceinline__ double pow2d(int e) {
-  e = max(-1022, min(1023, e));
-  return __hiloint2double((e + 1023) << 20, 0);
-}
+/* 2^e as a double for e in the normal range [-1022, 1023] (the guard keeps the kernel inside it) */
+__device__ __forceinline__ double pow2d(int e) { return __hiloint2double((e + 1023) << 20, 0); }
 
 /* byte offset of element (row r < 128, k byte kb < 32) inside a canonical 4 KiB tile */
 __host__ __device__ __forceinline__ int tile_offset(int r, int kb) { return (r >> 3) * 256 + (kb >> 4) * 128 + (r & 7) * 16 + (kb & 15); }
@@ -157,9 +175,148 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                : "memory");
 }
 
-template <int S_T, bool BAL = false>
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+/* groups of pass PS: G_HI .. G_LO, digits 1 .. D_HI take part */
+template <int PS>
+struct Pass {
+  static constexpr int G_HI = S + 1 - GROUPS_PER_PASS * PS;
+  static constexpr int G_LO = (G_HI - GROUPS_PER_PASS + 1) > 2 ? (G_HI - GROUPS_PER_PASS + 1) : 2;
+  static constexpr int D_HI = (G_HI - 1) < S ? (G_HI - 1) : S;
+  static constexpr int SUB = (2 * D_HI <= S) ? 2 : 1; /* a pass that needs <= half the digit slots packs 2 k steps per stage */
+};
+
+/* All MMAs of one 32-byte k step of pass PS: straight-line code with immediate descriptor offsets, t-major so that the first
+ * MMA into every accumulator of the pass is a t = 1 product (with g <= S + 1 every group starts at t = 1). */
+template <int PS>
+__device__ __forceinline__ void issue_kstep(uint32_t tmem_base, uint64_t da0, uint64_t db0, uint32_t first) {
+  constexpr int G_HI = Pass<PS>::G_HI, G_LO = Pass<PS>::G_LO;
+  const uint32_t idesc1 = idesc_i8(BM, BN), idesc2 = idesc_i8(BM, 2 * BN);
+#pragma unroll
+  for (int t = 1; t <= S; ++t) {
+    const int u_lo = (G_LO - t) > 1 ? (G_LO - t) : 1;
+    const int u_hi = (G_HI - t) < S ? (G_HI - t) : S;
+#pragma unroll
+    for (int u = 1; u <= S; ++u) {
+      if (u < u_lo || u > u_hi) continue;
+      if ((u - u_lo) & 1) continue; /* covered by the N = 256 MMA issued for u - 1 */
+      const bool pair = u + 1 <= u_hi;
+      umma_i8(tmem_base + (uint32_t)(t + u - G_LO) * BN, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)), db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)),
+              pair ? idesc2 : idesc1, t > 1 ? 1u : first);
+    }
+  }
+}
+
+/* producer side of one pass of one tile */
+template <int PS>
+__device__ __forceinline__ void load_pass(const Params &p, const int8_t *ta, const int8_t *tb, uint32_t smem_base, uint32_t full0, uint32_t empty0,
+                                          int &stage, uint32_t &phase) {
+  constexpr int D_HI = Pass<PS>::D_HI, SUB = Pass<PS>::SUB;
+  constexpr uint32_t bytes = (uint32_t)D_HI * TILE_BYTES;
+  constexpr size_t step_bytes = (size_t)S * TILE_BYTES;
+  for (int ks = 0; ks < p.ksteps; ks += SUB) {
+    const int nsub = min(SUB, p.ksteps - ks);
+    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+    const uint32_t full = full0 + 8 * stage;
+    mbar_expect_tx(full, 2 * bytes * nsub);
+    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+    for (int h = 0; h < nsub; ++h) {
+      bulk_load(sa + h * D_HI * SLOT_BYTES, ta + (size_t)(ks + h) * step_bytes, bytes, full);
+      bulk_load(sa + (S + h * D_HI) * SLOT_BYTES, tb + (size_t)(ks + h) * step_bytes, bytes, full);
+    }
+    if (++stage == STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+}
+
+/* MMA side of one pass of one tile */
+template <int PS>
+__device__ __forceinline__ void mma_pass(const Params &p, uint32_t tmem_base, uint32_t smem_base, uint32_t full0, uint32_t empty0, uint32_t tfull,
+                                         uint32_t tempty, uint32_t unit, int &stage, uint32_t &phase) {
+  constexpr int D_HI = Pass<PS>::D_HI, SUB = Pass<PS>::SUB;
+  mbar_wait(tempty, (unit & 1) ^ 1); /* the epilogue has drained the accumulators of the previous pass */
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  for (int ks = 0; ks < p.ksteps; ks += SUB) {
+    const int nsub = min(SUB, p.ksteps - ks);
+    if (!(p.flags & 2)) mbar_wait(full0 + 8 * stage, phase);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+    if (elect_one()) {
+      for (int h = 0; h < nsub; ++h) {
+        const uint64_t da0 = smem_desc_kmajor_noswz(sa + h * D_HI * SLOT_BYTES);
+        const uint64_t db0 = smem_desc_kmajor_noswz(sa + (S + h * D_HI) * SLOT_BYTES);
+        issue_kstep<PS>(tmem_base, da0, db0, (ks + h) > 0 ? 1u : 0u);
+      }
+      if (!(p.flags & 2)) umma_commit(empty0 + 8 * stage);
+    }
+    __syncwarp();
+    if (++stage == STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+  if (elect_one()) umma_commit(tfull);
+  __syncwarp();
+}
+
+/* epilogue of one pass of one tile (one of the four epilogue warps = 32 rows): C += 2^(eA+eB-..) * sum_g 256^(G_HI-g) P_g */
+template <int PS>
+__device__ __forceinline__ void epilogue_pass(const Params &p, uint32_t tmem_base, uint32_t tfull, uint32_t tempty, uint32_t unit, uint32_t tr,
+                                              int quarter, int lane, int tn, int row0, int rows_here, int ea) {
+  constexpr int G_HI = Pass<PS>::G_HI, G_LO = Pass<PS>::G_LO;
+  constexpr int SCALE = -2 * BAL_BITS + DIGIT_BITS * (2 * S - G_HI); /* weight of group G_HI relative to 2^(eA+eB) */
+  mbar_wait(tfull, unit & 1);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    if (tn * BN + c0 >= p.N || rows_here <= 0) break;
+    double acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+#pragma unroll
+    for (int g = G_HI; g >= G_LO; --g) {
+      int v[32];
+      tmem_ld_32x32b_x32(tlane + (uint32_t)(g - G_LO) * BN + c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const double w = pow2d(DIGIT_BITS * (G_HI - g));
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]); /* exact: |sum| < 2^53 */
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) asm volatile("st.shared.f64 [%0], %1;" ::"r"(tr + (uint32_t)(lane * 33 + j) * 8), "d"(acc[j]) : "memory");
+    __syncwarp();
+    const int col = tn * BN + c0 + lane;
+    const int eb = (col < p.N) ? __ldg(p.eB + col) : ZERO_EXP;
+    double *cptr = p.C + (long long)row0 * p.ldc + col;
+    const bool col_ok = eb != ZERO_EXP && !(p.flags & 1);
+    /* all 32 row loads of this lane's column are issued before any is used: one memory
+     * round trip per 32x32 block instead of four */
+    double cold[32];
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) cold[rr] = (col_ok && rr < rows_here) ? cptr[(long long)rr * p.ldc] : 0.0;
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      double x;
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(tr + (uint32_t)(rr * 33 + lane) * 8) : "memory");
+      const int er = __shfl_sync(0xffffffffu, ea, rr);
+      if (col_ok && rr < rows_here && er != ZERO_EXP && x != 0.0) cptr[(long long)rr * p.ldc] = cold[rr] + x * pow2d(er + eb + SCALE);
+    }
+    __syncwarp();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tempty);
+}
+
 __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) {
-  constexpr int DB = BAL ? 8 : DIGIT_BITS; /* bits between consecutive digit groups */
+  if (p.guard && *p.guard != 0) return; /* uniform over the grid: this chunk goes to the native-FP64 kernel */
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
@@ -171,8 +328,6 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
-  const int S = S_T > 0 ? S_T : p.S; /* compile-time digit count: the MMA issue loops unroll into straight-line uniform code */
-  const int npass = (S + GROUPS_PER_PASS - 1) / GROUPS_PER_PASS;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -199,105 +354,37 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
     if (lane == 0 && !(p.flags & 2)) {
       int stage = 0;
       uint32_t phase = 0;
-      const size_t step_bytes = (size_t)S * TILE_BYTES;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      constexpr size_t step_bytes = (size_t)S * TILE_BYTES;
+      int wave = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++wave) {
         int tm, tn;
         tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
         const int8_t *ta = p.TA + (size_t)tm * p.ksteps * step_bytes;
         const int8_t *tb = p.TB + (size_t)tn * p.ksteps * step_bytes;
-        for (int ps = 0; ps < npass; ++ps) {
-          const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
-          const int d_hi = min(S, g_hi - 1);                      /* digits 1 .. d_hi take part in this pass */
-          const uint32_t bytes = (uint32_t)d_hi * TILE_BYTES;
-          const int sub = (2 * d_hi <= MAX_S) ? 2 : 1;            /* a pass that needs <= half the digit slots packs 2 k steps per stage */
-          for (int ks = 0; ks < p.ksteps; ks += sub) {
-            const int nsub = min(sub, p.ksteps - ks);
-            mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            const uint32_t full = full0 + 8 * stage;
-            mbar_expect_tx(full, 2 * bytes * nsub);
-            const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            for (int h = 0; h < nsub; ++h) {
-              bulk_load(sa + h * d_hi * SLOT_BYTES, ta + (size_t)(ks + h) * step_bytes, bytes, full);
-              bulk_load(sa + (MAX_S + h * d_hi) * SLOT_BYTES, tb + (size_t)(ks + h) * step_bytes, bytes, full);
-            }
-            if (p.prefetch > 0 && ks + p.prefetch < p.ksteps) { /* pull the digits of a later k step into L2 */
-              for (int h = 0; h < nsub; ++h) {
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ta + (size_t)(ks + h + p.prefetch) * step_bytes), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(tb + (size_t)(ks + h + p.prefetch) * step_bytes), "r"(bytes) : "memory");
-              }
-            }
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
+        if (p.tstamp) p.tstamp[2 * (size_t)tile] = globaltimer_ns();
+        if (!(p.flags & 4)) {
+          /* all CTAs of this wave start streaming their panels together (every CTA is resident: grid <= SM count) */
+          unsigned int *ctr = p.wave_sync + wave;
+          const unsigned int expect = (unsigned int)min((long long)gridDim.x, (long long)total_tiles - (long long)wave * gridDim.x);
+          atomicAdd(ctr, 1u);
+          unsigned int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+          } while (seen < expect);
         }
+        load_pass<0>(p, ta, tb, smem_base, full0, empty0, stage, phase);
+        load_pass<1>(p, ta, tb, smem_base, full0, empty0, stage, phase);
       }
     }
   } else if (warp == 1) {
     /* ===== MMA issuer: the whole warp walks the loops (uniform control flow and addresses), one
-     * elected lane issues tcgen05.mma / tcgen05.commit.  With the loops inside `if (lane == 0)` every
-     * MMA cost ~140-180 cycles of register->uniform-register traffic (tools/umma_rate.cu). ===== */
-    {
-      const uint32_t idesc = idesc_i8(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t unit = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int ps = 0; ps < npass; ++ps, ++unit) {
-          const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
-          const int g_lo = max(2, g_hi - GROUPS_PER_PASS + 1);
-          mbar_wait(tempty, (unit & 1) ^ 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int d_hi = min(S, g_hi - 1);
-          const int sub = (2 * d_hi <= MAX_S) ? 2 : 1;
-          for (int ks = 0; ks < p.ksteps; ks += sub) {
-            const int nsub = min(sub, p.ksteps - ks);
-            if (!(p.flags & 2)) mbar_wait(full0 + 8 * stage, phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = smem_base + stage * STAGE_BYTES;
-            if (elect_one()) {
-              for (int h = 0; h < nsub; ++h) {
-                const uint64_t da0 = smem_desc_kmajor_noswz(sa + h * d_hi * SLOT_BYTES);
-                const uint64_t db0 = smem_desc_kmajor_noswz(sa + (MAX_S + h * d_hi) * SLOT_BYTES);
-                const uint32_t first = (ks + h) > 0 ? 1u : 0u;
-                if (S_T > 0) {
-                  /* fully unrolled: every (group, digit pair) of the pass with immediate descriptor offsets */
-#pragma unroll
-                  for (int gi = 0; gi < GROUPS_PER_PASS; ++gi) {
-#pragma unroll
-                    for (int t = 1; t <= MAX_S; ++t) {
-                      const int g = g_hi - gi;
-                      const int u = g - t;
-                      if (g >= g_lo && t <= S && u >= 1 && u <= S)
-                        umma_i8(tmem_base + (uint32_t)(g - g_lo) * BN, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)),
-                                    db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc, (t > max(1, g - S)) ? 1u : first);
-                    }
-                  }
-                } else {
-                  for (int g = g_hi; g >= g_lo; --g) {
-                    const uint32_t tacc = tmem_base + (uint32_t)(g - g_lo) * BN;
-                    const int t_lo = max(1, g - S), t_hi = min(S, g - 1);
-                    for (int t = t_lo; t <= t_hi; ++t) {
-                      const int u = g - t;
-                      umma_i8(tacc, da0 + (uint64_t)((t - 1) * (SLOT_BYTES >> 4)), db0 + (uint64_t)((u - 1) * (SLOT_BYTES >> 4)), idesc,
-                                  (t > t_lo) ? 1u : first);
-                    }
-                  }
-                }
-              }
-              if (!(p.flags & 2)) umma_commit(empty0 + 8 * stage);
-            }
-            __syncwarp();
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-          if (elect_one()) umma_commit(tfull);
-          __syncwarp();
-        }
-      }
+     * elected lane issues tcgen05.mma / tcgen05.commit ===== */
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t unit = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mma_pass<0>(p, tmem_base, smem_base, full0, empty0, tfull, tempty, unit++, stage, phase);
+      mma_pass<1>(p, tmem_base, smem_base, full0, empty0, tfull, tempty, unit++, stage, phase);
     }
   } else {
     /* ===== epilogue: combine the groups of a pass exactly, then one C += per element ===== */
@@ -311,57 +398,9 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
       const int my_row = row0 + lane;
       const int ea = (my_row < p.M) ? p.eA[my_row] : ZERO_EXP;
       const int rows_here = min(32, p.M - row0);
-      for (int ps = 0; ps < npass; ++ps, ++unit) {
-        const int g_hi = S + 1 - GROUPS_PER_PASS * ps;
-        const int g_lo = max(2, g_hi - GROUPS_PER_PASS + 1);
-        mbar_wait(tfull, unit & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          if (tn * BN + c0 >= p.N || rows_here <= 0) break;
-          double acc[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-          for (int g = g_hi; g >= g_lo; --g) {
-            int v[32];
-            tmem_ld_32x32b_x32(tlane + (uint32_t)(g - g_lo) * BN + c0, v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const double w = pow2d(DB * (g_hi - g));
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            asm volatile("st.shared.f64 [%0], %1;" ::"r"(tr + (uint32_t)(lane * 33 + j) * 8), "d"(acc[j]) : "memory");
-          __syncwarp();
-          const int col = tn * BN + c0 + lane;
-          const int eb = (col < p.N) ? __ldg(p.eB + col) : ZERO_EXP;
-          double *cptr = p.C + (long long)row0 * p.ldc + col;
-          const bool col_ok = eb != ZERO_EXP && !(p.flags & 1);
-          /* all 32 row loads of this lane's column are issued before any is used: one memory
-           * round trip per 32x32 block instead of four */
-          double cold[32];
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) cold[rr] = (col_ok && rr < rows_here) ? cptr[(long long)rr * p.ldc] : 0.0;
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            double x;
-            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(tr + (uint32_t)(rr * 33 + lane) * 8) : "memory");
-            const int er = __shfl_sync(0xffffffffu, ea, rr);
-            if (col_ok && rr < rows_here) {
-              if (er == NONFINITE_EXP || eb == NONFINITE_EXP)
-                cptr[(long long)rr * p.ldc] = __longlong_as_double(0x7ff8000000000000ll); /* Inf/NaN in the row or column */
-              else if (er != ZERO_EXP && x != 0.0)
-                cptr[(long long)rr * p.ldc] = cold[rr] + x * pow2d(BAL ? er + eb - 2 * BAL_BITS + 8 * (2 * S - g_hi) : er + eb - DIGIT_BITS * g_hi);
-            }
-          }
-          __syncwarp();
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty);
-      }
+      epilogue_pass<0>(p, tmem_base, tfull, tempty, unit++, tr, quarter, lane, tn, row0, rows_here, ea);
+      epilogue_pass<1>(p, tmem_base, tfull, tempty, unit++, tr, quarter, lane, tn, row0, rows_here, ea);
+      if (p.tstamp && warp == 2 && lane == 0) p.tstamp[2 * (size_t)tile + 1] = globaltimer_ns();
     }
   }
 
@@ -372,7 +411,6 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
-
 
 }  // namespace oz
 }  // namespace phpc

@@ -10,7 +10,6 @@
 #include "../../include/phpc_gemm.cuh"
 #include "dmma_gemm.cuh"
 #include "ozaki_gemm.cuh"
-#include "ozaki_gemm2.cuh"
 #include "ozaki_split.cuh"
 #include "phpc_internal.h"
 
@@ -70,8 +69,8 @@ DeviceCtx *phpc_ctx(int device) {
   CUDA_CHECK(cudaEventCreate(&ctx->ev0));
   CUDA_CHECK(cudaEventCreate(&ctx->ev1));
   CUDA_CHECK(cudaFuncSetAttribute(phpc::dmma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::GEMM_SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
-  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
+  CUDA_CHECK(cudaFuncSetAttribute(phpc::oz::ozaki_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, phpc::oz::SMEM_BYTES));
+  CUDA_CHECK(cudaEventCreateWithFlags(&ctx->gemm_done, cudaEventDisableTiming));
   load_driver_entry_points();
   ctx->ready = true;
   return ctx;
@@ -124,6 +123,10 @@ extern "C" void phpc_b200_finalize(void) {
     if (ctx->ozA.ptr) cudaFree(ctx->ozA.ptr);
     if (ctx->ozB.ptr) cudaFree(ctx->ozB.ptr);
     if (ctx->ozE.ptr) cudaFree(ctx->ozE.ptr);
+    if (ctx->ozSync.ptr) cudaFree(ctx->ozSync.ptr);
+    if (ctx->ozG.ptr) cudaFree(ctx->ozG.ptr);
+    cudaEventDestroy(ctx->gemm_done);
+    if (ctx->ozT.ptr) cudaFree(ctx->ozT.ptr);
     cudaFree(ctx->sched);
     cublasDestroy(ctx->blas);
     cudaEventDestroy(ctx->ev0);
@@ -206,26 +209,20 @@ static void encode_map_2d(CUtensorMap *map, const double *base, long long inner,
   }
 }
 
-/* A digit store of the Ozaki kernels seen as rows of 2 KiB (256 x 8-byte elements, no swizzle): a box of `box_rows` rows is
- * one contiguous range, so the tensor-map copy of the experimental 2cta-tma kernel writes the same shared-memory image as
- * the plain bulk copy of the other kernels. */
-static void encode_store_map(CUtensorMap *map, const void *base, size_t bytes, int box_rows) {
-  PHPC_REQUIRE(bytes % 2048 == 0 && box_rows >= 1 && box_rows <= 256, "digit store is not a whole number of 2 KiB rows");
-  cuuint64_t gdim[2] = {256, (cuuint64_t)(bytes / 2048)};
-  cuuint64_t gstride[1] = {2048};
-  cuuint32_t box[2] = {256, (cuuint32_t)box_rows};
-  cuuint32_t estride[2] = {1, 1};
-  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    char msg[160];
-    snprintf(msg, sizeof msg, "CUresult %d (digit store of %zu bytes, box of %d rows)", (int)r, bytes, box_rows);
-    phpc_die("cuTensorMapEncodeTiled", msg, __FILE__, __LINE__);
-  }
+/* Every GEMM launch of a device is ordered after the previous one, whatever stream it was given: the tile-scheduler words,
+ * the digit stores / exponents / guard of the tcgen05 path and its wave counters are per-device scratch, and two persistent
+ * grids that each wait for all of their CTAs to be resident must never share the SMs. */
+static void gemm_order_begin(DeviceCtx *ctx, cudaStream_t stream) {
+  if (ctx->gemm_in_flight && ctx->gemm_last_stream != stream) CUDA_CHECK(cudaStreamWaitEvent(stream, ctx->gemm_done, 0));
+}
+static void gemm_order_end(DeviceCtx *ctx, cudaStream_t stream) {
+  CUDA_CHECK(cudaEventRecord(ctx->gemm_done, stream));
+  ctx->gemm_in_flight = true;
+  ctx->gemm_last_stream = stream;
 }
 
-int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
-                     int k, int n, int ctas, cudaStream_t stream) {
+static int launch_dmma_guarded(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
+                               int k, int n, int ctas, cudaStream_t stream, const int *guard) {
   if (m <= 0 || n <= 0 || k <= 0) return 0; /* C += 0 */
   PHPC_REQUIRE(lda >= k && ldb >= n && ldc >= n, "leading dimension smaller than the row length");
   CUtensorMap tmA, tmB;
@@ -242,6 +239,7 @@ int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const doub
   p.tiles_n = (n + phpc::BN - 1) / phpc::BN;
   p.k_iters = (k + phpc::BK - 1) / phpc::BK;
   p.sched = ctx->sched;
+  p.guard = guard;
   const long long tiles = (long long)p.tiles_m * p.tiles_n;
   PHPC_REQUIRE(tiles < (1ll << 30), "too many output tiles for the 32-bit tile counter");
   int grid = (ctas <= 1) ? ctx->sm_count : (ctas < ctx->sm_count ? ctas : ctx->sm_count);
@@ -251,146 +249,105 @@ int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const doub
   return 1;
 }
 
-/* ------------------------------------------------------------------------- */
-/* Ozaki (int8 tcgen05) launcher                                              */
-/* ------------------------------------------------------------------------- */
-/* Bring-up aid of the experimental 2-CTA kernel (PHPC_OZ_PROGRESS=1): 8 host-mapped words per CTA in which every
- * warp role records how far it got (ozaki_gemm2.cuh, progress_mark).  The host can read them while a kernel hangs:
- * tools/ozaki_variants.py launches, polls phpc_compute_stream_idle() and dumps phpc_oz_progress_read() on a timeout. */
-/* Which digit scheme and kernel phpc_launch_ozaki uses: the environment, else the built-in default.  The defaults are
- * the round-1 kernel (8 truncated 7-bit digits, 1-CTA); flipping them after the variants have been validated on
- * hardware is a change of these two strings. */
-#define PHPC_OZAKI_DEFAULT_DIGITS "trunc" /* "trunc" | "balanced" */
-#define PHPC_OZAKI_DEFAULT_KERNEL "1cta"  /* "1cta" | "2cta" | "2cta-tma" */
-struct OzakiChoice {
-  bool balanced;
-  int kernel; /* 0 = 1-CTA, 1 = 2-CTA with relay warp, 2 = 2-CTA with tensor-map loads */
-};
-static OzakiChoice ozaki_choice() {
-  const char *dg = getenv("PHPC_OZAKI_DIGITS"), *kn = getenv("PHPC_OZAKI_KERNEL");
-  if (!dg || !*dg) dg = PHPC_OZAKI_DEFAULT_DIGITS;
-  if (!kn || !*kn) kn = PHPC_OZAKI_DEFAULT_KERNEL;
-  OzakiChoice c;
-  PHPC_REQUIRE(!strcmp(dg, "trunc") || !strcmp(dg, "balanced"), "PHPC_OZAKI_DIGITS must be trunc or balanced");
-  PHPC_REQUIRE(!strcmp(kn, "1cta") || !strcmp(kn, "2cta") || !strcmp(kn, "2cta-tma"), "PHPC_OZAKI_KERNEL must be 1cta, 2cta or 2cta-tma");
-  c.balanced = !strcmp(dg, "balanced");
-  c.kernel = !strcmp(kn, "2cta") ? 1 : (!strcmp(kn, "2cta-tma") ? 2 : 0);
-  return c;
-}
-/* What the Ozaki path of this process computes with (for bench.py's description of the arithmetic): digits per operand,
- * int8 digit products per FP64 product, kernel (0 / 1 / 2 as above), balanced base-256 digits or truncated 7-bit ones. */
-extern "C" void phpc_ozaki_config(int *digits, int *products, int *kernel, int *balanced) {
-  const OzakiChoice c = ozaki_choice();
-  int s = 7;
-  if (!c.balanced) {
-    const char *e = getenv("PHPC_OZAKI_SLICES");
-    s = (e && *e) ? atoi(e) : 8;
+int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
+                     int k, int n, int ctas, cudaStream_t stream) {
+  if (m <= 0 || n <= 0 || k <= 0) return 0;
+  gemm_order_begin(ctx, stream);
+  /* K chunks of 4096: the persistent CTAs of one launch drift apart over thousands of k iterations and the panel re-reads
+   * then miss L2 (1.5 TB of DRAM traffic for one N = 32768 launch, profiles/ncu_dmma_n32768_dram_r01.csv); between chunks
+   * the grid re-synchronises for free.  The per-element sum still runs in ascending k. */
+  int launches = 0;
+  const int kc_max = 4096;
+  for (int k0 = 0; k0 < k; k0 += kc_max) {
+    const int kc = (k - k0 < kc_max) ? k - k0 : kc_max;
+    launches += launch_dmma_guarded(ctx, dA + k0, lda, dB + (long long)k0 * ldb, ldb, dC, ldc, m, kc, n, ctas, stream, nullptr);
   }
-  if (digits) *digits = s;
-  if (products) *products = s * (s + 1) / 2;
-  if (kernel) *kernel = c.kernel;
-  if (balanced) *balanced = c.balanced ? 1 : 0;
+  gemm_order_end(ctx, stream);
+  return launches;
 }
 
-static unsigned int *g_oz_progress = nullptr;
-static int g_oz_progress_words = 0;
-static unsigned int *oz_progress_buffer(int ctas) {
-  const char *e = getenv("PHPC_OZ_PROGRESS");
-  if (!(e && *e && atoi(e) != 0)) return nullptr;
-  if (!g_oz_progress) {
-    g_oz_progress_words = 8 * ctas;
-    CUDA_CHECK(cudaHostAlloc((void **)&g_oz_progress, g_oz_progress_words * sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable));
-  }
-  memset(g_oz_progress, 0, g_oz_progress_words * sizeof(unsigned int));
-  unsigned int *dev = nullptr;
-  CUDA_CHECK(cudaHostGetDevicePointer((void **)&dev, g_oz_progress, 0));
-  return dev;
+/* ------------------------------------------------------------------------- */
+/* tcgen05 (Ozaki, int8) launcher                                             */
+/* ------------------------------------------------------------------------- */
+extern "C" void phpc_ozaki_config(int *digits, int *products, int *k_chunk, int *max_spread) {
+  if (digits) *digits = phpc::oz::S;
+  if (products) *products = phpc::oz::PRODUCTS;
+  if (k_chunk) *k_chunk = phpc::oz::KC_MAX;
+  if (max_spread) *max_spread = phpc::oz::MAX_SPREAD;
 }
-extern "C" int phpc_oz_progress_read(unsigned int *out, int max_words) {
-  if (!g_oz_progress) return 0;
-  const int n = g_oz_progress_words < max_words ? g_oz_progress_words : max_words;
-  for (int i = 0; i < n; ++i) out[i] = ((volatile unsigned int *)g_oz_progress)[i];
+
+static long long g_oz_tstamp_tiles = 0;
+/* diagnostics (PHPC_OZ_TSTAMP=1): per tile of the LAST launch, globaltimer ns at the start of its loads and at the end of its epilogue */
+extern "C" long long phpc_oz_tstamp_read(unsigned long long *out, long long max_tiles) {
+  DeviceCtx *ctx = phpc_cur_ctx();
+  CUDA_CHECK(cudaDeviceSynchronize());
+  const long long n = g_oz_tstamp_tiles < max_tiles ? g_oz_tstamp_tiles : max_tiles;
+  if (n > 0 && ctx->ozT.ptr) CUDA_CHECK(cudaMemcpy(out, ctx->ozT.ptr, (size_t)n * 16, cudaMemcpyDeviceToHost));
   return n;
 }
-extern "C" int phpc_compute_stream_idle(void) {
+/* How many K chunks of the tcgen05 path the guard handed to the native-FP64 kernel since the last call (synchronises the device). */
+extern "C" long long phpc_ozaki_fallback_chunks(void) {
   DeviceCtx *ctx = phpc_cur_ctx();
-  const cudaError_t e = cudaStreamQuery(ctx->compute);
-  if (e == cudaSuccess) return 1;
-  if (e == cudaErrorNotReady) return 0;
-  phpc_die("cudaStreamQuery(compute)", cudaGetErrorString(e), __FILE__, __LINE__);
+  CUDA_CHECK(cudaDeviceSynchronize());
+  if (!ctx->ozG.ptr) return 0;
+  int words[2] = {0, 0};
+  CUDA_CHECK(cudaMemcpy(words, (int *)ctx->ozG.ptr + 1, sizeof words, cudaMemcpyDeviceToHost));
+  CUDA_CHECK(cudaMemset((int *)ctx->ozG.ptr + 1, 0, sizeof words));
+  return words[0];
 }
+__global__ void guard_count_kernel(int *g) { /* g[0] = guard of the chunk, g[1] = chunks sent to the native kernel, g[2] = OR of their reasons */
+  if (g[0] != 0) {
+    g[1] += 1;
+    g[2] |= g[0];
+  }
+}
+
 int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
-                      int k, int n, int slices, cudaStream_t stream) {
+                      int k, int n, cudaStream_t stream) {
   using namespace phpc::oz;
   if (m <= 0 || n <= 0 || k <= 0) return 0;
   PHPC_REQUIRE(lda >= k && ldb >= n && ldc >= n, "leading dimension smaller than the row length");
-  if (slices <= 0) {
-    const char *e = getenv("PHPC_OZAKI_SLICES");
-    slices = (e && *e) ? atoi(e) : 8;
-  }
-  /* EXPERIMENTAL, opt-in, not validated on hardware in round 1 (tools/ozaki_variants.py validates them):
-   *   PHPC_OZAKI_DIGITS=balanced  7 balanced base-256 digits: 28 digit products instead of 36
-   *   PHPC_OZAKI_KERNEL=2cta      CTA pairs, cta_group::2 MMAs with M = 256 (ozaki_gemm2.cuh)
-   *   PHPC_OZAKI_KERNEL=2cta-tma  the same with cp.async.bulk.tensor.cta_group::2 loads instead of the relay warp */
-  OzakiChoice choice = ozaki_choice();
-  const bool balanced = choice.balanced;
-  const bool two_cta_tma = choice.kernel == 2; /* same kernel, operands loaded through tensor maps (ozaki_gemm2.cuh) */
-  const bool two_cta = choice.kernel != 0;
-  if (balanced) slices = 7;
-  PHPC_REQUIRE(!two_cta || slices == (balanced ? 7 : 8), "the 2-CTA kernel is built for 8 truncated or 7 balanced digits");
-  PHPC_REQUIRE(slices >= 2 && slices <= MAX_SLICES, "PHPC_OZAKI_SLICES must be in 2..8");
-  /* int32 accumulation of a whole group is exact while  K * S * 127^2 < 2^31  (S = 8: K <= 16643; 7 balanced digits,
-   * |digit| <= 128: K <= 18724).  Default K chunk 8192; PHPC_OZ_KC (multiple of 128, <= 16384) trades digit-store
-   * size for half as many epilogues (the C read-modify-write is ~5 % of a chunk at 8192). */
-  int kc_max = 8192;
-  {
-    const char *e = getenv("PHPC_OZ_KC");
-    if (e && *e) {
-      kc_max = atoi(e);
-      PHPC_REQUIRE(kc_max >= 128 && kc_max <= 16384 && kc_max % 128 == 0, "PHPC_OZ_KC must be a multiple of 128 in 128..16384");
-    }
-  }
+  gemm_order_begin(ctx, stream);
   int launches = 0;
   const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
   const long long tiles = (long long)tiles_m * tiles_n;
   PHPC_REQUIRE(tiles < (1ll << 30), "too many output tiles");
-  const int tiles_m_store = two_cta ? (tiles_m + 1) / 2 * 2 : tiles_m; /* a CTA pair works on two row tiles: pad with a zero tile */
-  const size_t m_pad = (size_t)tiles_m_store * BM, n_pad = (size_t)tiles_n * BN;
-  const char *pf = getenv("PHPC_OZ_PF"), *fl = getenv("PHPC_OZ_FLAGS"); /* diagnostics, see profiles/ozaki_experiments_r01.md */
-  for (int k0 = 0; k0 < k; k0 += kc_max) {
-    const int kc = (k - k0 < kc_max) ? k - k0 : kc_max;
+  const size_t m_pad = (size_t)tiles_m * BM, n_pad = (size_t)tiles_n * BN;
+  const char *fl = getenv("PHPC_OZ_FLAGS"), *ts = getenv("PHPC_OZ_TSTAMP"); /* diagnostics only (tools/ozaki_knobs.py) */
+  int grid = ctx->sm_count;
+  if ((long long)grid > tiles) grid = (int)tiles;
+  const size_t waves = (size_t)((tiles + grid - 1) / grid);
+  if (!ctx->ozG.ptr) {
+    phpc_buf_reserve(&ctx->ozG, 64);
+    CUDA_CHECK(cudaMemsetAsync(ctx->ozG.ptr, 0, 64, stream));
+  }
+  int *guard = (int *)ctx->ozG.ptr;
+  for (int k0 = 0; k0 < k; k0 += KC_MAX) {
+    const int kc = (k - k0 < KC_MAX) ? k - k0 : KC_MAX;
     const int kp = (kc + 127) / 128 * 128;
-    int8_t *TA = (int8_t *)phpc_buf_reserve(&ctx->ozA, (size_t)slices * m_pad * kp);
-    int8_t *TB = (int8_t *)phpc_buf_reserve(&ctx->ozB, (size_t)slices * n_pad * kp);
-    int *eA = (int *)phpc_buf_reserve(&ctx->ozE, ((size_t)m + n) * sizeof(int));
-    int *eB = eA + m;
+    int8_t *TA = (int8_t *)phpc_buf_reserve(&ctx->ozA, (size_t)S * m_pad * kp);
+    int8_t *TB = (int8_t *)phpc_buf_reserve(&ctx->ozB, (size_t)S * n_pad * kp);
+    int *eA = (int *)phpc_buf_reserve(&ctx->ozE, 2 * ((size_t)m + n) * sizeof(int)); /* maxima of A, of B, then the minima */
+    int *eB = eA + m, *eminA = eA + m + n, *eminB = eminA + m;
+    unsigned int *wave_sync = (unsigned int *)phpc_buf_reserve(&ctx->ozSync, (waves + 1) * sizeof(unsigned int));
     const double *a = dA + k0;
     const double *b = dB + (long long)k0 * ldb;
-    exp_init_kernel<<<(m + n + 255) / 256, 256, 0, stream>>>(eA, m + n);
+    CUDA_CHECK(cudaMemsetAsync(wave_sync, 0, (waves + 1) * sizeof(unsigned int), stream));
+    exp_init_kernel<<<(2 * (m + n) + 255) / 256, 256, 0, stream>>>(eA, m + n, guard);
     {
       const int segs = (kc + 1023) / 1024;
       const long long units = (long long)m * segs;
-      row_exp_kernel<<<(unsigned)((units + 7) / 8), 256, 0, stream>>>(a, lda, m, kc, eA);
-      dim3 grid((n + 255) / 256, (kc + 63) / 64);
-      col_exp_kernel<<<grid, 256, 0, stream>>>(b, ldb, kc, n, eB);
+      row_exp_kernel<<<(unsigned)((units + 7) / 8), 256, 0, stream>>>(a, lda, m, kc, eA, eminA, guard);
+      dim3 cgrid((n + 255) / 256, (kc + 63) / 64);
+      col_exp_kernel<<<cgrid, 256, 0, stream>>>(b, ldb, kc, n, eB, eminB, guard);
+      guard_kernel<<<1, 1024, 0, stream>>>(eA, eminA, m, eB, eminB, n, guard);
+      guard_count_kernel<<<1, 1, 0, stream>>>(guard);
     }
     {
       const long long threads = (long long)m_pad * (kp / 16);
-      dim3 grid((unsigned)((n_pad + 127) / 128), kp / 32);
-      if (balanced || two_cta) {
-        const unsigned a_blocks = (unsigned)((threads + 255) / 256);
-        const int halves = two_cta ? 2 : 1;
-        if (balanced) {
-          split_a_tiled_v2_kernel<true, 7><<<a_blocks, 256, 0, stream>>>(a, lda, m, (int)m_pad, kc, kp, eA, TA);
-          split_b_tiled_v2_kernel<true, 7><<<grid, 128, 0, stream>>>(b, ldb, kc, n, (int)n_pad, kp, eB, TB, halves);
-        } else {
-          split_a_tiled_v2_kernel<false, 8><<<a_blocks, 256, 0, stream>>>(a, lda, m, (int)m_pad, kc, kp, eA, TA);
-          split_b_tiled_v2_kernel<false, 8><<<grid, 128, 0, stream>>>(b, ldb, kc, n, (int)n_pad, kp, eB, TB, halves);
-        }
-      } else {
-        split_a_tiled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, kc, kp, eA, TA, slices);
-        split_b_tiled_kernel<<<grid, 128, 0, stream>>>(b, ldb, kc, n, kp, eB, TB, slices);
-      }
+      dim3 bgrid((unsigned)((n_pad + 127) / 128), kp / 32);
+      split_a_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, (int)m_pad, kc, kp, eA, TA, guard);
+      split_b_kernel<<<bgrid, 128, 0, stream>>>(b, ldb, kc, n, (int)n_pad, kp, eB, TB, guard);
     }
     Params p;
     p.C = dC;
@@ -398,61 +355,26 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     p.M = m;
     p.N = n;
     p.ksteps = kp / BKB;
-    p.S = slices;
     p.eA = eA;
     p.eB = eB;
     p.tiles_m = tiles_m;
     p.tiles_n = tiles_n;
     p.TA = TA;
     p.TB = TB;
-    p.prefetch = (pf && *pf) ? atoi(pf) : 0;
+    p.guard = guard;
+    p.wave_sync = wave_sync;
     p.flags = (fl && *fl) ? atoi(fl) : 0;
-    p.progress = two_cta ? oz_progress_buffer(ctx->sm_count) : nullptr;
-    if (balanced || two_cta) { /* experimental kernels opt in to their shared memory here, not at context creation:
-                                * nothing about them may affect the default path */
-      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_kernel<7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<7, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-      CUDA_CHECK(cudaFuncSetAttribute(ozaki_gemm_2cta_kernel<7, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    p.tstamp = nullptr;
+    if (ts && atoi(ts)) {
+      p.tstamp = (unsigned long long *)phpc_buf_reserve(&ctx->ozT, (size_t)tiles * 16);
+      g_oz_tstamp_tiles = (long long)tiles;
     }
-    if (two_cta) {
-      p.tiles_m = tiles_m_store;
-      const long long pair_tiles = (long long)(tiles_m_store / 2) * tiles_n;
-      long long clusters = ctx->sm_count / 2;
-      if (clusters > pair_tiles) clusters = pair_tiles;
-      const int grid2 = (int)(2 * clusters); /* __cluster_dims__(2,1,1): CTAs 2c and 2c+1 form pair c */
-      StoreMaps maps;
-      memset(&maps, 0, sizeof maps);
-      if (two_cta_tma) {
-        const size_t a_bytes = (size_t)slices * m_pad * kp, b_bytes = (size_t)slices * n_pad * kp;
-        for (int ps = 0; ps < 2; ++ps) { /* pass 0 stages every digit, pass 1 the first slices - 4 */
-          const int d = ps == 0 ? slices : slices - GROUPS_PER_PASS;
-          encode_store_map(&maps.a[ps], TA, a_bytes, 2 * d);
-          encode_store_map(&maps.b[ps], TB, b_bytes, d);
-        }
-        if (balanced)
-          ozaki_gemm_2cta_kernel<7, true, true><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p, maps);
-        else
-          ozaki_gemm_2cta_kernel<8, false, true><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p, maps);
-      } else if (balanced) {
-        ozaki_gemm_2cta_kernel<7, true, false><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p, maps);
-      } else {
-        ozaki_gemm_2cta_kernel<8, false, false><<<grid2, THREADS, SMEM2_BYTES, stream>>>(p, maps);
-      }
-    } else {
-      int grid = ctx->sm_count;
-      if ((long long)grid > tiles) grid = (int)tiles;
-      if (balanced)
-        ozaki_gemm_kernel<7, true><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
-      else if (slices == 8)
-        ozaki_gemm_kernel<8><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
-      else
-        ozaki_gemm_kernel<0><<<grid, THREADS, SMEM_BYTES, stream>>>(p);
-    }
+    ozaki_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(p);
     CUDA_CHECK(cudaGetLastError());
-    launches += 6;
+    /* the same chunk on the native-FP64 kernel, which only runs when the guard is set (and the kernel above returned at once) */
+    launches += 8 + launch_dmma_guarded(ctx, a, lda, b, ldb, dC, ldc, m, kc, n, 0, stream, guard);
   }
+  gemm_order_end(ctx, stream);
   return launches;
 }
 
@@ -478,9 +400,9 @@ extern "C" void phpc_gemm_device_cublas(const double *dA, long long lda, const d
 }
 
 extern "C" int phpc_gemm_device_ozaki(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
-                                      int k, int n, int slices, void *stream) {
+                                      int k, int n, void *stream) {
   DeviceCtx *ctx = phpc_cur_ctx();
-  return phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, slices, stream ? (cudaStream_t)stream : ctx->compute);
+  return phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, stream ? (cudaStream_t)stream : ctx->compute);
 }
 
 extern "C" float phpc_gemm_device_timed(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
@@ -492,7 +414,7 @@ extern "C" float phpc_gemm_device_timed(const double *dA, long long lda, const d
     if (use_cublas == 1)
       phpc_launch_cublas(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctx->compute);
     else if (use_cublas == 2)
-      phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, 0, ctx->compute);
+      phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctx->compute);
     else
       phpc_launch_dmma(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctas, ctx->compute);
   }
@@ -561,7 +483,7 @@ extern "C" int phpc_default_backend(void) { return phpc_use_ozaki() ? 2 : 0; }
 static void launch_dmma_adapter(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC,
                                 long long ldc, int m, int k, int n, int ctas, cudaStream_t s) {
   if (phpc_use_ozaki())
-    phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, 0, s);
+    phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, s);
   else
     phpc_launch_dmma(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctas, s);
 }

@@ -5,7 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#define PHPC_B200_VERSION 101 /* 101: phpc_host_plan, phpc_default_backend, phpc_ozaki_config, bring-up diagnostics */
+#define PHPC_B200_VERSION 200 /* 200 (round 2): one tcgen05 kernel (7 balanced digits, paired MMAs, wave start) + guard -> DMMA; phpc_gemm_device_ozaki lost `slices` */
 
 #define PHPC_MAX_DEVICES 16
 
@@ -52,6 +52,11 @@ struct DeviceCtx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   DevBuf bufA, bufB, bufC;
   DevBuf ozA, ozB, ozE; /* Ozaki digit matrices of the current K chunk and the row/column exponents */
+  DevBuf ozSync, ozT;   /* wave-sync counters; diagnostics: per-tile timestamps */
+  DevBuf ozG;           /* [0] guard of the current K chunk, [1] chunks handed to the native kernel, [2] OR of their reasons */
+  cudaEvent_t gemm_done = nullptr; /* recorded after every GEMM launch: launches of one device never overlap (shared scratch) */
+  bool gemm_in_flight = false;
+  cudaStream_t gemm_last_stream = nullptr;
 };
 
 DeviceCtx *phpc_ctx(int device); /* lazily created; makes `device` current */
@@ -61,10 +66,10 @@ void *phpc_buf_reserve(DevBuf *b, size_t bytes);
 /* enqueue the DMMA kernel on `stream`; returns launches (0 or 1) */
 int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                      int k, int n, int ctas, cudaStream_t stream);
-/* FP64 GEMM rebuilt from int8 tcgen05 MMAs (Ozaki scheme, `slices` 7-bit digits per operand,
- * <= 0 picks PHPC_OZAKI_SLICES or 8); returns the number of kernels launched */
+/* FP64 GEMM rebuilt from int8 tcgen05 MMAs (Ozaki scheme, 7 balanced base-256 digits per operand; K chunks the guard
+ * rejects run on the DMMA kernel); returns the number of kernels launched */
 int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
-                      int k, int n, int slices, cudaStream_t stream);
+                      int k, int n, cudaStream_t stream);
 bool phpc_use_ozaki(void); /* env PHPC_GEMM=ozaki */
 void phpc_launch_cublas(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                         int k, int n, cudaStream_t stream);

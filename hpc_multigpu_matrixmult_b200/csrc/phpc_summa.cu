@@ -582,7 +582,7 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
       phpc_launch_cublas(ctx, a, lda, b, s->ldn, s->dC, s->ldn, s->m, st.width, s->n, comp);
       ++launches;
     } else if (backend == PHPC_BACKEND_OZAKI) {
-      launches += phpc_launch_ozaki(ctx, a, lda, b, s->ldn, s->dC, s->ldn, s->m, st.width, s->n, 0, comp);
+      launches += phpc_launch_ozaki(ctx, a, lda, b, s->ldn, s->dC, s->ldn, s->m, st.width, s->n, comp);
     } else {
       int use = ctas;
       if (any_comm && !pull && comm_sms > 0 && q + 1 < nsteps) {
@@ -647,7 +647,7 @@ static int launch_local_gemm(phpc_summa *s, int backend, int ctas, const double 
     phpc_launch_cublas(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, st);
     return 1;
   }
-  if (backend == PHPC_BACKEND_OZAKI) return phpc_launch_ozaki(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, 0, st);
+  if (backend == PHPC_BACKEND_OZAKI) return phpc_launch_ozaki(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, st);
   return phpc_launch_dmma(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, ctas, st);
 }
 

@@ -50,9 +50,11 @@ void phpc_copy2d_to_device(double *dev, long long ld_dev, const double *host, lo
 /*
  * dC[m x n, ldc] += dA[m x k, lda] * dB[k x n, ldb] with the sm_100a DMMA kernel,
  * enqueued on `stream` (a cudaStream_t; NULL = the library's compute stream)
- * and NOT synchronised.  dA, dB must be 16-byte aligned with even lda, ldb (TMA
+ * and NOT synchronised.  GEMM launches of one device are ordered one after the other
+ * whatever stream they are given (they share per-device scratch); K is walked in
+ * chunks of 4096, one launch each.  dA, dB must be 16-byte aligned with even lda, ldb (TMA
  * global-stride rule); the call aborts otherwise.  `ctas` <= 0 means one
- * persistent CTA per SM.  Returns the number of kernels launched (1, or 0 for an
+ * persistent CTA per SM.  Returns the number of kernels launched (0 for an
  * empty problem).
  */
 int phpc_gemm_device(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m, int k, int n,
@@ -61,14 +63,19 @@ int phpc_gemm_device(const double *dA, long long lda, const double *dB, long lon
 void phpc_gemm_device_cublas(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m, int k,
                              int n, void *stream);
 /*
- * Same contraction on the tcgen05 tensor cores: A and B are cut into `slices` signed 7-bit
- * digit matrices (error-free, per-row / per-column power-of-two scaling), the digit products run
- * as int8 MMAs with exact int32 accumulators in TMEM, and the FP64 result is reassembled in the
- * epilogue (Ozaki scheme; slices <= 0 = PHPC_OZAKI_SLICES or 8, i.e. 56 bits below each row /
- * column maximum).  Inputs must be finite.  Returns the number of kernels launched.
+ * Same contraction on the tcgen05 tensor cores (the default local GEMM of the reference-named entry points): per K chunk of
+ * 8192, rows of A and columns of B are scaled by a power of two and written as 7 balanced base-256 digits (54 bits below the
+ * row / column maximum, error free up to that rounding), the 28 digit products with t + u <= 8 run as int8 MMAs with exact
+ * int32 accumulators in TMEM, and the FP64 result is reassembled in the epilogue (Ozaki scheme).  Error model: normwise per
+ * row of A / column of B, |dC_ij| <~ k * 2^-55 * max|A_i,:| * max|B_:,j| plus two FP64 roundings per chunk.  A guard computed
+ * with the exponents sends a K chunk to the native-FP64 DMMA kernel instead when it holds an Inf/NaN, when exponents come
+ * near the FP64 range limits (underflow / overflow then behave as in FP64), or when the nonzero entries of one row / column
+ * span more than 2^40 — so special values propagate exactly as in the reference.  Returns the number of kernels launched.
  */
 int phpc_gemm_device_ozaki(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m, int k,
-                           int n, int slices, void *stream);
+                           int n, void *stream);
+/* K chunks the guard handed to the native-FP64 kernel since the previous call (synchronises the device). */
+long long phpc_ozaki_fallback_chunks(void);
 /* Run phpc_gemm_device `reps` times back to back and return the mean device
  * milliseconds per launch (CUDA events on the launching stream). */
 float phpc_gemm_device_timed(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m, int k,
@@ -95,18 +102,13 @@ void phpc_fill_host(double *h, long long ld, long long rows, long long cols, lon
  * number for phpc_summa_run: PHPC_BACKEND_OZAKI (tcgen05, default) or PHPC_BACKEND_DMMA (environment PHPC_GEMM=dmma). */
 int phpc_default_backend(void);
 
-/* The configuration the tcgen05 (Ozaki) path of this process runs with (environment PHPC_OZAKI_DIGITS / PHPC_OZAKI_KERNEL /
- * PHPC_OZAKI_SLICES, else the built-in defaults): digits per operand, int8 digit products per FP64 product
- * (digits*(digits+1)/2), kernel 0 = 1-CTA, 1 = 2-CTA (relay), 2 = 2-CTA (tensor-map loads), balanced = 1 for balanced
- * base-256 digits (0: truncated 7-bit digits).  Any pointer may be NULL. */
-void phpc_ozaki_config(int *digits, int *products, int *kernel, int *balanced);
+/* The fixed arithmetic of the tcgen05 path: digits per operand (7), int8 digit products per FP64 product (28), K chunk (8192)
+ * and the largest exponent spread inside one row / column the guard accepts (40).  Any pointer may be NULL. */
+void phpc_ozaki_config(int *digits, int *products, int *k_chunk, int *max_spread);
 
-/* ---- bring-up diagnostics of the experimental 2-CTA kernel (PHPC_OZAKI_KERNEL=2cta, PHPC_OZ_PROGRESS=1) ---- */
-/* 1 when everything enqueued on the library's compute stream has finished, 0 while work is pending (never blocks). */
-int phpc_compute_stream_idle(void);
-/* Copies the host-mapped progress words (8 per CTA: producer, MMA issuer / relay, 4 epilogue warps, set-up) of the last
- * 2-CTA launch; works WHILE that kernel runs or hangs.  Returns the number of words written (0 when not enabled). */
-int phpc_oz_progress_read(unsigned int *out, int max_words);
+/* ---- diagnostics (tools/ozaki_knobs.py; environment PHPC_OZ_TSTAMP=1, PHPC_OZ_FLAGS) ---- */
+/* Per tile of the last tcgen05 launch: globaltimer ns at the start of its loads [2*tile] and the end of its epilogue [2*tile+1]. */
+long long phpc_oz_tstamp_read(unsigned long long *out, long long max_tiles);
 
 #ifdef __cplusplus
 }

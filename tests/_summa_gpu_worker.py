@@ -33,7 +33,7 @@ def main():
     # device-resident loop with its own chunking and on-device generation of the blocks
     s = capi.Summa(comm, N, kc)
     s.fill(fill)
-    st = s.run()
+    st = s.run(capi.BACKEND_DMMA)
     Cd = np.zeros((N, N))
     s.download_c(Cd, gather=True)
     # the same loop with the tcgen05 (Ozaki) local GEMM

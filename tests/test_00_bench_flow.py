@@ -24,15 +24,36 @@ class _Stats:
     total_ms, gemm_ms, exposed_ms, steps, launches, broadcasts, bytes_received = 10.0, 9.5, 0.5, 1, 6, 0, 0
 
 
+def _fake_value(seed, rows, cols, N):
+    """Position-based stand-in for the library's counter-based fill: any window regenerates the same values."""
+    flat = (np.asarray(rows, dtype=np.uint64)[:, None] * np.uint64(N) + np.asarray(cols, dtype=np.uint64)[None, :])
+    h = (flat * np.uint64(2654435761) + np.uint64(seed) * np.uint64(40503)) % np.uint64(1 << 32)
+    return h.astype(np.float64) / float(1 << 31) - 1.0
+
+
 class _FakeSumma:
+    wrong = False
+
     def __init__(self, comm, n, kc=0):
+        self.n = n
         self.block = (n, n)
+        self.coords = (0, 0)
+        self.dims = (1, 1)
 
     def fill(self, kind):
-        pass
+        idx = np.arange(self.n)
+        self.A = _fake_value(1234, idx, idx, self.n)
+        self.B = _fake_value(5678, idx, idx, self.n)
+        self.C = np.zeros((self.n, self.n))
 
     def run(self, backend, ctas, stream, stats=True):
+        self.C += self.A @ self.B
+        if self.wrong:
+            self.C[0, 0] += 1.0
         return _Stats() if stats else None
+
+    def read_c_block(self, row0=0, col0=0, rows=None, cols=None):
+        return self.C[row0:row0 + rows, col0:col0 + cols].copy()
 
     def destroy(self):
         pass
@@ -51,21 +72,17 @@ def _fake_capi(wrong_result=False):
     lib = _FakeLib()
 
     def fill_host(ptr, ld, rows, cols, row0, col0, N, kind, seed):
-        a = np.ctypeslib.as_array(ptr, shape=(rows * ld,))
-        rng = np.random.default_rng(seed + row0 * 7 + col0)
+        a = np.ctypeslib.as_array(ptr, shape=((rows - 1) * ld + cols,))
+        v = _fake_value(seed, np.arange(row0, row0 + rows), np.arange(col0, col0 + cols), N)
         for r in range(rows):
-            a[r * ld:r * ld + cols] = rng.uniform(-1, 1, cols)
+            a[r * ld:r * ld + cols] = v[r]
         return 0
 
     lib.phpc_fill_host = fill_host
     m.load = lambda: lib
 
     def ozaki_config():
-        import os
-
-        bal = os.environ.get("PHPC_OZAKI_DIGITS") == "balanced"
-        d = 7 if bal else 8
-        return {"digits": d, "products": d * (d + 1) // 2, "kernel": os.environ.get("PHPC_OZAKI_KERNEL", "1cta"), "balanced": bal}
+        return {"digits": 7, "products": 28, "k_chunk": 8192, "max_spread": 40}
 
     m.ozaki_config = ozaki_config
     m.mpi_init = lambda *a: None
@@ -143,6 +160,9 @@ def test_product_arm_prints_the_contract_line(monkeypatch, fake_cuda):
     e2e = line["e2e"]
     assert e2e["verified"] is True and e2e["value"] > 0 and e2e["h2d_bytes_per_step"] == 3 * 8 * 64 * 64 and e2e["d2h_bytes_per_step"] == 8 * 64 * 64
     assert line["gpu_launches"] == _Stats.launches * 2
+    assert line["value_verified"] is True and line["value_verify"]["elements_checked_per_rank"] >= 16
+    assert line["value_verify"]["passes_accumulated"] == 3  # 1 warm-up + 2 timed steps
+    assert e2e["verify"]["worst_error_over_bound"] < 1.0
     assert line["native_fp64_dmma"]["roofline"]["unit"] == "TFLOP/s"  # the second kernel is reported beside the first
 
 
@@ -152,19 +172,36 @@ def test_e2e_leg_refuses_to_report_a_wrong_result(monkeypatch, fake_cuda):
     assert e2e["verified"] is False and e2e["value"] is None
 
 
-def test_experimental_variants_change_the_reported_arithmetic(monkeypatch, fake_cuda):
+def test_value_verification_catches_a_wrong_device_result(monkeypatch, fake_cuda):
     import hpc_multigpu_matrixmult_b200 as pkg
 
-    monkeypatch.setattr(pkg, "capi", _fake_capi(), raising=False)
+    capi = _fake_capi()
+
+    class Wrong(_FakeSumma):
+        wrong = True
+
+    capi.Summa = Wrong
+    monkeypatch.setattr(pkg, "capi", capi, raising=False)
     monkeypatch.setitem(sys.modules, "hpc_multigpu_matrixmult_b200.capi", pkg.capi)
-    monkeypatch.setenv("PHPC_OZAKI_DIGITS", "balanced")
-    monkeypatch.setenv("PHPC_OZAKI_KERNEL", "2cta")
     out = io.StringIO()
     with redirect_stdout(out):
         bench.product_arm(_args(no_e2e=True, no_secondary=True))
     line = json.loads([l for l in out.getvalue().splitlines() if l.startswith("{")][0])
-    assert "28 int8 MMAs" in line["roofline"]["note"] and "2cta" in line["roofline"]["kernel"]
+    assert line["value_verified"] is False
+
+
+def test_roofline_counts_the_int8_products_of_the_fixed_arithmetic(monkeypatch, fake_cuda):
+    import hpc_multigpu_matrixmult_b200 as pkg
+
+    monkeypatch.setattr(pkg, "capi", _fake_capi(), raising=False)
+    monkeypatch.setitem(sys.modules, "hpc_multigpu_matrixmult_b200.capi", pkg.capi)
+    out = io.StringIO()
+    with redirect_stdout(out):
+        bench.product_arm(_args(no_e2e=True, no_secondary=True))
+    line = json.loads([l for l in out.getvalue().splitlines() if l.startswith("{")][0])
+    assert "28 int8 MMAs" in line["roofline"]["note"] and "tcgen05" in line["roofline"]["kernel"]
     assert line["roofline"]["ops_per_launch"] == 2.0 * 64 ** 3 * 28
+    assert "emulated FP64" in line["config"]["arithmetic"]
 
 
 def test_reference_arm_line(monkeypatch):

@@ -132,20 +132,11 @@ def test_csv_runner_reads_the_reference_config_format(built, tmp_path):
     assert b200.returncode == 0 and len(b200.stdout.strip().splitlines()) == 10
 
 
-def test_ozaki_config_follows_the_environment(capi, monkeypatch):
-    """phpc_ozaki_config / phpc_default_backend: one place decides what the tcgen05 path runs with (environment, else the
-    built-in defaults = the kernel that was validated on hardware in round 1)."""
-    for k in ("PHPC_OZAKI_DIGITS", "PHPC_OZAKI_KERNEL", "PHPC_OZAKI_SLICES", "PHPC_GEMM"):
-        monkeypatch.delenv(k, raising=False)
-    lib = capi.load()
-    assert capi.ozaki_config() == {"digits": 8, "products": 36, "kernel": "1cta", "balanced": False}
-    assert lib.phpc_default_backend() == capi.BACKEND_OZAKI
-    monkeypatch.setenv("PHPC_OZAKI_DIGITS", "balanced")
-    monkeypatch.setenv("PHPC_OZAKI_KERNEL", "2cta-tma")
-    assert capi.ozaki_config() == {"digits": 7, "products": 28, "kernel": "2cta-tma", "balanced": True}
-    monkeypatch.setenv("PHPC_OZAKI_DIGITS", "trunc")
-    monkeypatch.setenv("PHPC_OZAKI_KERNEL", "2cta")
-    monkeypatch.setenv("PHPC_OZAKI_SLICES", "6")
-    assert capi.ozaki_config() == {"digits": 6, "products": 21, "kernel": "2cta", "balanced": False}
+def test_ozaki_config_is_fixed(capi, monkeypatch):
+    """One tcgen05 kernel, one arithmetic: 7 balanced base-256 digits, 28 products, K chunks of 8192; only PHPC_GEMM=dmma
+    switches the reference-named entry points to the native-FP64 kernel."""
+    assert capi.ozaki_config() == {"digits": 7, "products": 28, "k_chunk": 8192, "max_spread": 40}
+    monkeypatch.delenv("PHPC_GEMM", raising=False)
+    assert capi.default_backend() == capi.BACKEND_OZAKI
     monkeypatch.setenv("PHPC_GEMM", "dmma")
-    assert lib.phpc_default_backend() == capi.BACKEND_DMMA
+    assert capi.default_backend() == capi.BACKEND_DMMA

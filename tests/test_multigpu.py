@@ -40,7 +40,7 @@ def test_summa_matches_reference_summa_seeded(gpu, oracle, tmp_path, grid, ngpu)
     A = oracle.fill(N, N, kind=1, seed=oracle.SEED_A)
     B = oracle.fill(N, N, kind=1, seed=oracle.SEED_B)
     want = oracle.summa(A, B, *grid)
-    for name, C in zip(("host-entry dmma", "host-entry cublas", "device-resident dmma", "device-resident ozaki"), Cs):
+    for name, C in zip(("host-entry tcgen05 (default)", "host-entry cublas", "device-resident dmma", "device-resident tcgen05"), Cs):
         assert oracle.rel_frobenius(C, want) <= 1e-14, name
     assert "bcasts=" in log
 
@@ -72,7 +72,7 @@ def test_nccl_broadcast_transport_equals_pull_transport(gpu, oracle, tmp_path):
     grid = (2, 2) if gpu.phpc_b200_device_count() >= 4 else (1, 2)
     a, _ = _run(grid, 384, 1, tmp_path, kc=50)
     b, _ = _run(grid, 384, 1, tmp_path, kc=50, env={"PHPC_PANEL": "nccl"})
-    for idx, name in ((0, "host-entry dmma"), (2, "device-resident dmma")):
+    for idx, name in ((0, "host-entry tcgen05 (default)"), (2, "device-resident dmma"), (3, "device-resident tcgen05")):
         diff = np.abs(a[idx] - b[idx])
         assert np.array_equal(a[idx], b[idx]), f"{name}: {np.count_nonzero(diff)} elements differ, max {diff.max():.3e}"
     # cuBLAS picks its kernel per call; only require agreement to rounding
