@@ -41,7 +41,7 @@ METRIC = "summa_gemm_tflops"
 UNIT = "TFLOP/s"
 GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
 CPU_SAMPLE_N = 1024
-DMMA_N32768_DRAM_BYTES = 1513196364800 + 8660417536  # one ncu capture of the N=32768 launch (profiles/ncu_dmma_n32768_dram_r01.csv)
+DMMA_N32768_DRAM_BYTES = 578.8e9 + 68.8e9  # ncu, the 8 K-chunk launches of one N=32768 GEMM (profiles/ncu_dmma_n32768_dram_r02.csv; one launch in r01: 1522 GB)
 
 
 # ----------------------------------------------------------------------------
@@ -333,7 +333,10 @@ def host_matrices(capi, N, dims, coords, pin=True):
     m, n = N // r, N // c
     A = np.empty((N, N), dtype=np.float64)
     B = np.empty((N, N), dtype=np.float64)
-    C = np.empty((N, N), dtype=np.float64)
+    # rank 0's C receives every block: in node-shared page-locked memory (phpc_host_malloc_shared) all ranks write their block
+    # into it over their own PCIe link; plain memory (the fallback when /dev/shm is too small) gives the serial gather
+    shared = capi.host_array_shared(N, N) if (r * c > 1 and pi == 0 and pj == 0) else None
+    C = shared[0] if shared else np.empty((N, N), dtype=np.float64)
     dp = capi.c_double_p
     lcm = r * c // __import__("math").gcd(r, c)
     pk = N // lcm
@@ -364,14 +367,16 @@ def host_matrices(capi, N, dims, coords, pin=True):
             regs.append((B.ctypes.data + (k * pk * N) * 8, pk * N * 8))
     regs.append((A.ctypes.data + (pi * m * N) * 8, m * N * 8))
     C[pi * m:(pi + 1) * m, pj * n:(pj + 1) * n] = 0.0
-    if pi == 0 and pj == 0:
+    if shared:
+        pass  # page-locked by the allocator
+    elif pi == 0 and pj == 0:
         regs.append((C.ctypes.data, N * N * 8))  # the gather root receives every block: keep its whole C page-locked
     else:
         regs.append((C.ctypes.data + (pi * m * N) * 8, m * N * 8))
     if pin:
         for ptr, nbytes in regs:
             L.phpc_host_register(ptr, nbytes)
-    return A, B, C, regs
+    return A, B, C, regs, (shared[1] if shared else None)
 
 
 def e2e_measure(args, capi, L, comm, dims, rank, world, barrier, max_over_ranks):
@@ -385,7 +390,7 @@ def e2e_measure(args, capi, L, comm, dims, rank, world, barrier, max_over_ranks)
     N = args.n
     flops = 2.0 * N ** 3
     coords = (rank // dims[1], rank % dims[1])
-    A, B, C, regs = host_matrices(capi, N, dims, coords)
+    A, B, C, regs, shared_c = host_matrices(capi, N, dims, coords)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     pi, pj = coords
     m_blk, n_blk = N // dims[0], N // dims[1]
@@ -426,13 +431,18 @@ def e2e_measure(args, capi, L, comm, dims, rank, world, barrier, max_over_ranks)
     for ptr, _ in regs:
         L.phpc_host_unregister(ptr)
     L.phpc_summa_release_cache()
+    gather = "n/a (one rank)" if world == 1 else ("parallel: rank 0's C in node-shared page-locked memory, every rank writes its block over its own PCIe link"
+                                                 if max_over_ranks(1.0 if (rank == 0 and shared_c) else 0.0) > 0 else "serial through rank 0's GPU and PCIe link")
+    if shared_c:
+        del C
+        L.phpc_host_free_shared(shared_c)
     bands = os.environ.get("PHPC_HOST_BANDS", "4 (default for blocks of >= 8192 rows)") if world == 1 else "n/a"
     return {"value": flops / secs / 1e12 if ok is not False else None, "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * N * N,
             "d2h_bytes_per_step": 8 * N * N, "ms_per_step": secs * 1e3, "steps": e2e_steps, "verified": ok,
             "verify": {"elements_checked_rank0": nsamples, "worst_error_over_bound": worst, "passes_accumulated": passes,
                        "how": "sampled C elements of every rank's block in rank 0's gathered host C (and each rank's own block) vs exactly summed FP64 "
                               "dot products of regenerated rows/columns; bound 4*sqrt(N)*2^-53*sum|a||b| per pass"},
-            "host_row_bands": bands,
+            "host_row_bands": bands, "gather": gather,
             "api": "phpc_gemm_summa_cuda(grid_comm, A, B, C, N, ...) on page-locked full N x N host matrices; owned blocks H2D, C block "
                    "H2D and D2H + gather to rank 0 inside the timed region (one GPU: C row bands pipelined under the GEMMs)"}
 
@@ -589,7 +599,9 @@ def product_arm(args):
                 roof["traffic"] = tr[0]
                 roof["traffic_source"] = (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of {tr[2]} at m,k,n = "
                                           f"{m_blk},{k_launch},{n_blk} ({tr[1]}); algorithmic bytes of that launch: "
-                                          f"{(m_blk + n_blk) * k_launch * slices + 4 * 8 * m_blk * n_blk} (digits read once + 2 passes of C read+write)")
+                                          f"{(m_blk + n_blk) * k_launch * slices + 4 * 8 * m_blk * n_blk} (digits read once + 2 passes of C read+write); with a "
+                                          "126 MB L2 each wave of 148 tiles has to stream its 16 + ~9 digit panels once: 443 waves x ~25 panels x 12 MiB "
+                                          "= 146 GB is the floor of this tiling")
                 roof.pop("traffic_note", None)
             sus = int8_sustained_peak()
             if sus:
@@ -608,8 +620,9 @@ def product_arm(args):
         else:
             roof = {"bound": "tensor", "achieved": gemm_tflops, "peak": fp64_pk, "unit": UNIT, "frac": gemm_tflops / fp64_pk,
                     "traffic": DMMA_N32768_DRAM_BYTES if (world == 1 and N == 32768 and st.steps == 1) else None,
-                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of this launch shape, profiles/ncu_dmma_n32768_dram_r01.csv "
-                                      "(compute bound: 12 % of HBM bandwidth; L2 hit rate of the A/B panel re-reads ~66 %)",
+                    "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 8 K-chunk launches (kc = 4096) of this GEMM, "
+                                      "profiles/ncu_dmma_n32768_dram_r02.csv; algorithmic bytes of the chunked GEMM: 8 x (A chunk 1.07 + B chunk 1.07 "
+                                      "+ C read+write 17.2 GB) = 155 GB (a single launch in round 1 moved 1522 GB)",
                     "kernel": "phpc::dmma_gemm_kernel (FP64 DMMA.8x8x4, TMA + mbarrier pipeline)",
                     "flops_per_launch": 2.0 * m_blk * n_blk * k_per_gemm, "kernel_ms": gemm_ms, "peak_source": fp64_src}
         return {"tflops": flops / (ms * 1e-3) / 1e12, "ms": ms, "clocks": clocks, "stats": st, "roofline": roof,

@@ -118,6 +118,9 @@ def load():
     L.phpc_host_malloc_pinned.argtypes = [ctypes.c_size_t]
     L.phpc_host_malloc_pinned.restype = ctypes.c_void_p
     L.phpc_host_free_pinned.argtypes = [ctypes.c_void_p]
+    L.phpc_host_malloc_shared.argtypes = [ctypes.c_size_t]
+    L.phpc_host_malloc_shared.restype = ctypes.c_void_p
+    L.phpc_host_free_shared.argtypes = [ctypes.c_void_p]
     L.phpc_host_register.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     L.phpc_host_unregister.argtypes = [ctypes.c_void_p]
     L.phpc_device_memset.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t]
@@ -235,6 +238,18 @@ def phpc_gemm_summa_cublas(grid_comm, A, B, C, gpu_count=1):
     t = ctypes.c_float(-1.0)
     load().phpc_gemm_summa_cublas(grid_comm, _dp(A), _dp(B), _dp(C), n, gpu_count, ctypes.byref(t))
     return t.value
+
+
+def host_array_shared(rows, cols):
+    """rows x cols float64 matrix in page-locked host memory that every rank of the node can map (phpc_host_malloc_shared):
+    as rank 0's C it makes the SUMMA gather parallel over all PCIe links.  Returns (array, pointer) or None when the
+    shared-memory file system cannot hold it; free with load().phpc_host_free_shared(pointer)."""
+    nbytes = rows * cols * 8
+    ptr = load().phpc_host_malloc_shared(nbytes)
+    if not ptr:
+        return None
+    buf = (ctypes.c_double * (rows * cols)).from_address(ptr)
+    return np.frombuffer(buf, dtype=np.float64).reshape(rows, cols), ptr
 
 
 def device_window(dev_ptr, ld, row0, col0, rows, cols):

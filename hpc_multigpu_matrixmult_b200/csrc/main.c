@@ -151,7 +151,10 @@ int main(int argc, char *argv[]) {
     const size_t elems = (size_t)N * (size_t)N;
     double *A = (double *)malloc(elems * sizeof(double));
     double *B = (double *)malloc(elems * sizeof(double));
-    double *C = (double *)malloc(elems * sizeof(double));
+    /* rank 0's C receives every block: in node-shared page-locked memory the gather runs over all PCIe links at once */
+    double *C = (rank == 0 && size > 1) ? (double *)phpc_host_malloc_shared(elems * sizeof(double)) : NULL;
+    const int c_shared = C != NULL;
+    if (!C) C = (double *)malloc(elems * sizeof(double));
     MPI_ASSERT(A != NULL);
     MPI_ASSERT(B != NULL);
     MPI_ASSERT(C != NULL);
@@ -180,7 +183,10 @@ int main(int argc, char *argv[]) {
     cublas_time = get_cur_time() - start_time;
     free(A);
     free(B);
-    free(C);
+    if (c_shared)
+      phpc_host_free_shared(C);
+    else
+      free(C);
   }
 
   /* mean kernel time over the ranks (reference src/main.c:97-98) */

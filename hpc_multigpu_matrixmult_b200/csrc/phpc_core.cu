@@ -161,6 +161,101 @@ extern "C" void *phpc_host_malloc_pinned(size_t bytes) {
 extern "C" void phpc_host_free_pinned(void *p) {
   if (p) CUDA_CHECK(cudaFreeHost(p));
 }
+/* ---- host memory that every rank of the node can map: lets all ranks write their C block straight into rank 0's result
+ * matrix over their own PCIe link (phpc_summa_download_c) instead of funnelling the gather through rank 0's GPU ---- */
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <string>
+#include <vector>
+struct SharedHost {
+  void *base;
+  size_t bytes;
+  std::string name;
+  bool owner;
+};
+static std::vector<SharedHost> g_shared;
+
+extern "C" void *phpc_host_malloc_shared(size_t bytes) {
+  phpc_cur_ctx();
+  static int counter = 0;
+  char name[64];
+  snprintf(name, sizeof name, "/phpc_host_%d_%d", (int)getpid(), counter++);
+  const size_t len = (bytes + 4095) / 4096 * 4096;
+  int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0) return nullptr;
+  if (posix_fallocate(fd, 0, (off_t)len) != 0) { /* reserve now: a full /dev/shm must not turn into SIGBUS later */
+    close(fd);
+    shm_unlink(name);
+    return nullptr;
+  }
+  void *p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) {
+    shm_unlink(name);
+    return nullptr;
+  }
+  CUDA_CHECK(cudaHostRegister(p, len, cudaHostRegisterPortable));
+  g_shared.push_back({p, len, name, true});
+  return p;
+}
+
+extern "C" void phpc_host_free_shared(void *p) {
+  for (size_t i = 0; i < g_shared.size(); ++i)
+    if (g_shared[i].base == p) {
+      cudaHostUnregister(p);
+      munmap(p, g_shared[i].bytes);
+      if (g_shared[i].owner) shm_unlink(g_shared[i].name.c_str());
+      g_shared.erase(g_shared.begin() + i);
+      return;
+    }
+}
+
+/* is [p, p + 1) inside a shared allocation OWNED by this process?  name (>= 64 bytes), offset of p and size of the allocation */
+int phpc_host_shared_lookup(const void *p, char *name, unsigned long long *offset, unsigned long long *bytes) {
+  for (const SharedHost &h : g_shared)
+    if (h.owner && (const char *)p >= (const char *)h.base && (const char *)p < (const char *)h.base + h.bytes) {
+      snprintf(name, 64, "%s", h.name.c_str());
+      *offset = (unsigned long long)((const char *)p - (const char *)h.base);
+      *bytes = h.bytes;
+      return 1;
+    }
+  return 0;
+}
+
+/* importer side: map another rank's shared allocation (cached by name); [off, off + len) of it is page-locked for this
+ * process' GPU on first use */
+void *phpc_host_shared_map(const char *name, unsigned long long bytes, unsigned long long off, unsigned long long len) {
+  struct Pinned {
+    std::string name;
+    size_t lo, hi;
+  };
+  static std::vector<Pinned> pinned;
+  void *base = nullptr;
+  for (const SharedHost &h : g_shared)
+    if (h.name == name) base = h.base;
+  if (!base) {
+    int fd = shm_open(name, O_RDWR, 0600);
+    PHPC_REQUIRE(fd >= 0, "cannot open the shared host allocation of the gather root");
+    base = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    PHPC_REQUIRE(base != MAP_FAILED, "cannot map the shared host allocation of the gather root");
+    g_shared.push_back({base, (size_t)bytes, name, false});
+  }
+  const size_t lo = off / 4096 * 4096, hi = (off + len + 4095) / 4096 * 4096 < bytes ? (off + len + 4095) / 4096 * 4096 : bytes;
+  bool have = false;
+  for (const Pinned &q : pinned)
+    if (q.name == name && q.lo <= lo && q.hi >= hi) have = true;
+  if (!have) {
+    phpc_cur_ctx();
+    CUDA_CHECK(cudaHostRegister((char *)base + lo, hi - lo, cudaHostRegisterPortable));
+    pinned.push_back({name, lo, hi});
+  }
+  return base;
+}
+
 extern "C" void phpc_host_register(void *p, size_t bytes) {
   phpc_cur_ctx();
   CUDA_CHECK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
@@ -303,7 +398,7 @@ __global__ void guard_count_kernel(int *g) { /* g[0] = guard of the chunk, g[1] 
 }
 
 int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
-                      int k, int n, cudaStream_t stream) {
+                      int k, int n, int ctas, cudaStream_t stream) {
   using namespace phpc::oz;
   if (m <= 0 || n <= 0 || k <= 0) return 0;
   PHPC_REQUIRE(lda >= k && ldb >= n && ldc >= n, "leading dimension smaller than the row length");
@@ -314,7 +409,8 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
   PHPC_REQUIRE(tiles < (1ll << 30), "too many output tiles");
   const size_t m_pad = (size_t)tiles_m * BM, n_pad = (size_t)tiles_n * BN;
   const char *fl = getenv("PHPC_OZ_FLAGS"), *ts = getenv("PHPC_OZ_TSTAMP"); /* diagnostics only (tools/ozaki_knobs.py) */
-  int grid = ctx->sm_count;
+  /* grid_width x grid_height of the reference's CLI = number of persistent CTAs (<= 1: one per SM), as for the DMMA kernel */
+  int grid = (ctas <= 1) ? ctx->sm_count : (ctas < ctx->sm_count ? ctas : ctx->sm_count);
   if ((long long)grid > tiles) grid = (int)tiles;
   const size_t waves = (size_t)((tiles + grid - 1) / grid);
   if (!ctx->ozG.ptr) {
@@ -372,7 +468,7 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     ozaki_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(p);
     CUDA_CHECK(cudaGetLastError());
     /* the same chunk on the native-FP64 kernel, which only runs when the guard is set (and the kernel above returned at once) */
-    launches += 8 + launch_dmma_guarded(ctx, a, lda, b, ldb, dC, ldc, m, kc, n, 0, stream, guard);
+    launches += 8 + launch_dmma_guarded(ctx, a, lda, b, ldb, dC, ldc, m, kc, n, ctas, stream, guard);
   }
   gemm_order_end(ctx, stream);
   return launches;
@@ -402,7 +498,7 @@ extern "C" void phpc_gemm_device_cublas(const double *dA, long long lda, const d
 extern "C" int phpc_gemm_device_ozaki(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                                       int k, int n, void *stream) {
   DeviceCtx *ctx = phpc_cur_ctx();
-  return phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, stream ? (cudaStream_t)stream : ctx->compute);
+  return phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, 0, stream ? (cudaStream_t)stream : ctx->compute);
 }
 
 extern "C" float phpc_gemm_device_timed(const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
@@ -414,7 +510,7 @@ extern "C" float phpc_gemm_device_timed(const double *dA, long long lda, const d
     if (use_cublas == 1)
       phpc_launch_cublas(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctx->compute);
     else if (use_cublas == 2)
-      phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctx->compute);
+      phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctas, ctx->compute);
     else
       phpc_launch_dmma(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctas, ctx->compute);
   }
@@ -483,7 +579,7 @@ extern "C" int phpc_default_backend(void) { return phpc_use_ozaki() ? 2 : 0; }
 static void launch_dmma_adapter(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC,
                                 long long ldc, int m, int k, int n, int ctas, cudaStream_t s) {
   if (phpc_use_ozaki())
-    phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, s);
+    phpc_launch_ozaki(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctas, s);
   else
     phpc_launch_dmma(ctx, dA, lda, dB, ldb, dC, ldc, m, k, n, ctas, s);
 }
@@ -529,8 +625,17 @@ static float host_gemm(launch_fn launch, const double *a, int lda, const double 
     CUDA_CHECK(cudaEventRecord(ctx->ev0, s));
     launch(ctx, dA, pa, dB, pb, dC, pc, m, k, dev_n, ctas, s);
     CUDA_CHECK(cudaEventRecord(ctx->ev1, s));
-    CUDA_CHECK(cudaMemcpy2DAsync(c + col, (size_t)ldc * sizeof(double), dC, pc * sizeof(double), (size_t)dev_n * sizeof(double), m,
-                                 cudaMemcpyDeviceToHost, s));
+    col += dev_n;
+  }
+  /* downloads in a second loop: a D2H into pageable memory returns only when it has finished, which would keep GPU g+1 from
+   * even starting its upload until GPU g is completely done (the kernels of all GPUs are in flight by now) */
+  col = 0;
+  for (int gi = 0; gi < gpu_count; ++gi) {
+    const int dev_n = n / gpu_count + (gi < n % gpu_count);
+    DeviceCtx *ctx = phpc_ctx(first + gi);
+    const long long pc = phpc_pad_ld(dev_n);
+    CUDA_CHECK(cudaMemcpy2DAsync(c + col, (size_t)ldc * sizeof(double), ctx->bufC.ptr, pc * sizeof(double), (size_t)dev_n * sizeof(double), m,
+                                 cudaMemcpyDeviceToHost, ctx->compute));
     col += dev_n;
   }
   float total_ms = 0.f;

@@ -69,9 +69,13 @@ int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const doub
 /* FP64 GEMM rebuilt from int8 tcgen05 MMAs (Ozaki scheme, 7 balanced base-256 digits per operand; K chunks the guard
  * rejects run on the DMMA kernel); returns the number of kernels launched */
 int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
-                      int k, int n, cudaStream_t stream);
+                      int k, int n, int ctas, cudaStream_t stream);
 bool phpc_use_ozaki(void); /* env PHPC_GEMM=ozaki */
 void phpc_launch_cublas(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                         int k, int n, cudaStream_t stream);
+
+/* shared host allocations (phpc_host_malloc_shared): owner-side lookup and importer-side mapping, used by the gather */
+int phpc_host_shared_lookup(const void *p, char *name, unsigned long long *offset, unsigned long long *bytes);
+void *phpc_host_shared_map(const char *name, unsigned long long bytes, unsigned long long off, unsigned long long len);
 
 static inline long long phpc_pad_ld(long long cols) { return (cols + 15) / 16 * 16; }

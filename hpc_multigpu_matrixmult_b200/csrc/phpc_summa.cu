@@ -176,7 +176,8 @@ struct phpc_summa {
   size_t ringA_elems = 0, ringB_elems = 0;
   std::vector<cudaEvent_t> ev_bcast, ev_free; /* per ring slot */
   std::vector<cudaEvent_t> ev_g0, ev_g1;      /* per step: GEMM start / stop */
-  std::vector<cudaEvent_t> ev_up;             /* per step: owned chunks uploaded (host-sourced runs) */
+  std::vector<cudaEvent_t> ev_up;             /* per step: owned chunks uploaded (host-sourced runs); interprocess events on a multi-rank pull grid */
+  std::vector<cudaEvent_t> peer_up_a, peer_up_b; /* per step: the A / B root's ev_up of that step, opened through CUDA IPC (null when own) */
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_user = nullptr, ev_cup = nullptr;
 };
 
@@ -207,7 +208,9 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   s->m = n / s->r;
   s->n = n / s->c;
   s->pk = n / s->lcm;
-  if (kc <= 0) kc = env_int("PHPC_KC", s->size == 1 ? s->pk : 4096);
+  /* multi-rank default 8192 = the K chunk of the tcgen05 launcher: one set of exponent / split kernels and two C passes per
+   * transferred chunk (4096 doubled both per flop); the ring buffers stay below 2 GiB per slot up to N = 65536 on 2 x 4 */
+  if (kc <= 0) kc = env_int("PHPC_KC", s->size == 1 ? s->pk : 8192);
   if (kc > s->pk) kc = s->pk;
   s->kc = kc;
   s->ldn = phpc_pad_ld(s->n);
@@ -357,7 +360,26 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   for (int q = 0; q < nsteps; ++q) {
     CUDA_CHECK(cudaEventCreate(&s->ev_g0[q]));
     CUDA_CHECK(cudaEventCreate(&s->ev_g1[q]));
-    CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_up[q], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_up[q], cudaEventDisableTiming | ((s->size > 1 && s->transport == 1) ? cudaEventInterprocess : 0)));
+  }
+  s->peer_up_a.assign(nsteps, nullptr);
+  s->peer_up_b.assign(nsteps, nullptr);
+  if (s->size > 1 && s->transport == 1) {
+    /* "owned chunks of step q are in my store" as an event the peers that pull the chunk can wait for on THEIR streams:
+     * host-sourced runs upload chunk by chunk under the GEMMs instead of "upload everything, synchronise, barrier" */
+    std::vector<cudaIpcEventHandle_t> mine(nsteps), theirs(nsteps);
+    for (int q = 0; q < nsteps; ++q) CUDA_CHECK(cudaIpcGetEventHandle(&mine[q], s->ev_up[q]));
+    for (int root = 0; root < s->size; ++root) {
+      if (root == s->rank) theirs = mine;
+      MPI_Bcast(theirs.data(), (int)(sizeof(cudaIpcEventHandle_t) * nsteps), MPI_BYTE, root, grid_comm);
+      if (root == s->rank) continue;
+      const int ri = root / s->c, rj = root % s->c;
+      for (int q = 0; q < nsteps; ++q) {
+        const phpc_summa_step &st = s->steps[q];
+        if (ri == s->pi && rj == st.a_root && !st.own_a) CUDA_CHECK(cudaIpcOpenEventHandle(&s->peer_up_a[q], theirs[q]));
+        if (rj == s->pj && ri == st.b_root && !st.own_b) CUDA_CHECK(cudaIpcOpenEventHandle(&s->peer_up_b[q], theirs[q]));
+      }
+    }
   }
   CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_cup, cudaEventDisableTiming));
   CUDA_CHECK(cudaEventCreate(&s->ev_begin));
@@ -394,6 +416,10 @@ extern "C" void phpc_summa_destroy(phpc_summa *s) {
   for (cudaEvent_t e : s->ev_g0) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_g1) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_up) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->peer_up_a)
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->peer_up_b)
+    if (e) cudaEventDestroy(e);
   cudaEventDestroy(s->ev_cup);
   cudaEventDestroy(s->ev_begin);
   cudaEventDestroy(s->ev_end);
@@ -491,24 +517,30 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
   }
   CUDA_CHECK(cudaEventRecord(s->ev_begin, comp));
   CUDA_CHECK(cudaStreamWaitEvent(comm, s->ev_begin, 0));
-  if (host_src) {
-    CUDA_CHECK(cudaStreamWaitEvent(copy, s->ev_begin, 0));
-    upload_c(s, hC, copy);
-    CUDA_CHECK(cudaEventRecord(s->ev_cup, copy));
-    CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_cup, 0));
-  }
-
   const bool any_comm = (s->r > 1 || s->c > 1);
   const bool pull = any_comm && s->transport == 1;
   cudaStream_t comm2 = ctx->comm2;
-  if (pull) {
-    CUDA_CHECK(cudaStreamWaitEvent(comm2, s->ev_begin, 0));
-    if (host_src) {
-      /* peers pull straight from this rank's store: make all of it valid, everywhere, first */
-      for (int q = 0; q < nsteps; ++q) upload_step(s, q, hA, hB, copy);
-      CUDA_CHECK(cudaStreamSynchronize(copy));
+  if (pull) CUDA_CHECK(cudaStreamWaitEvent(comm2, s->ev_begin, 0));
+  if (host_src) {
+    CUDA_CHECK(cudaStreamWaitEvent(copy, s->ev_begin, 0));
+    if (pull) {
+      /* Peers pull straight from this rank's store.  All uploads are enqueued now, in step order (step 0 first, then the C
+       * block, then the rest), each followed by an interprocess event; the host barrier only orders the ENQUEUE of those
+       * records before the peers enqueue their waits - the copies themselves run under the GEMMs of earlier steps. */
+      for (int q = 0; q < nsteps; ++q) {
+        upload_step(s, q, hA, hB, copy);
+        CUDA_CHECK(cudaEventRecord(s->ev_up[q], copy));
+        if (q == 0) {
+          upload_c(s, hC, copy);
+          CUDA_CHECK(cudaEventRecord(s->ev_cup, copy));
+        }
+      }
       MPI_Barrier(s->grid_comm);
+    } else {
+      upload_c(s, hC, copy);
+      CUDA_CHECK(cudaEventRecord(s->ev_cup, copy));
     }
+    CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_cup, 0));
   }
   /* stage-in of step q = upload of the owned chunks (host-sourced) + the panel transfers */
   auto stage_in = [&](int q) {
@@ -519,6 +551,7 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
       if (s->c > 1 && !st.own_a) {
         const size_t count = (size_t)s->m * phpc_pad_ld(st.width);
         if (q >= s->nbuf) CUDA_CHECK(cudaStreamWaitEvent(comm, s->ev_free[slot], 0));
+        if (host_src) CUDA_CHECK(cudaStreamWaitEvent(comm, s->peer_up_a[q], 0)); /* the owner's upload of this chunk has landed */
         CUDA_CHECK(cudaMemcpyAsync(s->ringA + (size_t)slot * s->ringA_elems, s->peerA[st.a_root] + s->root_a_off[q], count * 8,
                                    cudaMemcpyDeviceToDevice, comm));
         ++broadcasts;
@@ -528,6 +561,7 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
       if (s->r > 1 && !st.own_b) {
         const size_t count = (size_t)st.width * s->ldn;
         if (q >= s->nbuf) CUDA_CHECK(cudaStreamWaitEvent(comm2, s->ev_free[slot], 0));
+        if (host_src) CUDA_CHECK(cudaStreamWaitEvent(comm2, s->peer_up_b[q], 0));
         CUDA_CHECK(cudaMemcpyAsync(s->ringB + (size_t)slot * s->ringB_elems, s->peerB[st.b_root] + s->root_b_off[q], count * 8,
                                    cudaMemcpyDeviceToDevice, comm2));
         ++broadcasts;
@@ -571,6 +605,7 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
     if (any_comm) {
       CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_bcast[slot], 0));
       if (pull) CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_bcast2[slot], 0));
+      if (pull && host_src && (st.own_a || st.own_b)) CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_up[q], 0));
     } else if (host_src) {
       CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_up[q], 0));
     }
@@ -582,7 +617,7 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
       phpc_launch_cublas(ctx, a, lda, b, s->ldn, s->dC, s->ldn, s->m, st.width, s->n, comp);
       ++launches;
     } else if (backend == PHPC_BACKEND_OZAKI) {
-      launches += phpc_launch_ozaki(ctx, a, lda, b, s->ldn, s->dC, s->ldn, s->m, st.width, s->n, comp);
+      launches += phpc_launch_ozaki(ctx, a, lda, b, s->ldn, s->dC, s->ldn, s->m, st.width, s->n, ctas, comp);
     } else {
       int use = ctas;
       if (any_comm && !pull && comm_sms > 0 && q + 1 < nsteps) {
@@ -647,7 +682,7 @@ static int launch_local_gemm(phpc_summa *s, int backend, int ctas, const double 
     phpc_launch_cublas(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, st);
     return 1;
   }
-  if (backend == PHPC_BACKEND_OZAKI) return phpc_launch_ozaki(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, st);
+  if (backend == PHPC_BACKEND_OZAKI) return phpc_launch_ozaki(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, ctas, st);
   return phpc_launch_dmma(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, ctas, st);
 }
 
@@ -828,6 +863,31 @@ extern "C" void phpc_summa_download_c(phpc_summa *s, double *C, int gather) {
   /* own block -> own place (every rank keeps its block at its global offset, reference :44) */
   CUDA_CHECK(cudaMemcpy2DAsync(C + (size_t)s->pi * s->m * N + (size_t)s->pj * s->n, N * sizeof(double), s->dC, s->ldn * sizeof(double),
                                row_bytes, s->m, cudaMemcpyDeviceToHost, st));
+  if (s->transport == 1) {
+    /* Parallel gather: when rank 0's C lives in memory every rank can map (phpc_host_malloc_shared), every rank writes its
+     * block into it over its OWN PCIe link, all links at once; rank 0's link carries one block instead of all of them. */
+    struct {
+      int shared;
+      char name[64];
+      unsigned long long off, bytes;
+    } info;
+    memset(&info, 0, sizeof info);
+    if (s->rank == 0) info.shared = phpc_host_shared_lookup(C, info.name, &info.off, &info.bytes);
+    MPI_Bcast(&info, (int)sizeof info, MPI_BYTE, 0, s->grid_comm);
+    if (info.shared) {
+      if (s->rank != 0) {
+        const unsigned long long blk_off = info.off + ((unsigned long long)s->pi * s->m * N + (unsigned long long)s->pj * s->n) * sizeof(double);
+        const unsigned long long blk_len = ((unsigned long long)(s->m - 1) * N + s->n) * sizeof(double);
+        char *base = (char *)phpc_host_shared_map(info.name, info.bytes, blk_off, blk_len);
+        CUDA_CHECK(cudaMemcpy2DAsync(base + blk_off, N * sizeof(double), s->dC, s->ldn * sizeof(double), row_bytes, s->m, cudaMemcpyDeviceToHost,
+                                     ctx->copy));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->copy));
+      }
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      MPI_Barrier(s->grid_comm); /* every block has landed in rank 0's C */
+      return;
+    }
+  }
   if (s->transport == 1) {
     /* pull transport: the root copies each peer's finished C block out of the peer's HBM */
     CUDA_CHECK(cudaStreamSynchronize(st));

@@ -40,6 +40,13 @@ void phpc_host_free_pinned(void *p);
 /* Page-lock / unlock a caller-owned host range so copies from it are asynchronous DMA. */
 void phpc_host_register(void *p, size_t bytes);
 void phpc_host_unregister(void *p);
+/* Page-locked host memory that every rank of the node can map (POSIX shared memory).  When rank 0's result matrix C lives in
+ * such an allocation, the gather of phpc_gemm_summa_cuda / phpc_summa_download_c lets every rank write its C block into it
+ * over its OWN PCIe link (all links in parallel) instead of sending all blocks through rank 0's GPU (the reference's serial
+ * gather, src/phpc_summa.c:97-110).  Returns NULL when the shared-memory file system cannot hold `bytes` (use malloc then:
+ * the result is the same, only the gather is serial). */
+void *phpc_host_malloc_shared(size_t bytes);
+void phpc_host_free_shared(void *p);
 void phpc_device_memset(void *p, int value, size_t bytes);
 void phpc_device_synchronize(void);
 /* rows x cols doubles between a host matrix (ld_host) and a device matrix (ld_dev); synchronous. */
