@@ -93,7 +93,7 @@ def run_reference_summa_all_cores(n=4096):
                       "restatement of the reference kernel's per-element loop (gcc -O2), host-memory broadcasts included"}
 
 
-def run_reference_cuda_build(n=8192, tile=32, gw=64, gh=64, timeout=300):
+def run_reference_cuda_build(n=8192, tile=32, gw=64, gh=64, timeout=300, ranks=1):
     """The reference's OWN CUDA+MPI program on this box: oracle/_ref/ref_main.out = /root/reference/src/{main.c, phpc_summa.c,
     phpc_gemm.cu, utils.c} compiled unchanged against the MPI shim (oracle/Makefile), one rank, one GPU.  It times its CUDA pass
     (host-memory SUMMA + H2D + gemm_kernel + D2H, src/main.c:93-95) and its cuBLASXt pass (:105-107) itself and writes the
@@ -107,9 +107,15 @@ def run_reference_cuda_build(n=8192, tile=32, gw=64, gh=64, timeout=300):
         return {"unavailable": "oracle/_ref/ref_main.out or bin/mpirun not built"}
     with tempfile.TemporaryDirectory() as tmp:
         os.makedirs(os.path.join(tmp, "csv"))
-        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+        if ranks == 1:
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+        else:  # the reference uses EVERY visible GPU in every rank (src/main.c:54-56): one GPU per rank through the launcher
+            env = dict(os.environ, PHPC_GPU_POLICY="visible", PHPC_GPUS=str(ranks))
+            env.pop("CUDA_VISIBLE_DEVICES", None)
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "PHPC_MPI_SHM", "PHPC_MPI_RANK", "PHPC_MPI_SIZE"):
+            env.pop(k, None)  # the child world is the launcher's, not torchrun's
         try:
-            p = subprocess.run([mpirun, "-n", "1", exe, str(n), str(tile), str(gw), str(gh), "bench"], cwd=tmp, env=env, capture_output=True,
+            p = subprocess.run([mpirun, "-n", str(ranks), exe, str(n), str(tile), str(gw), str(gh), "bench"], cwd=tmp, env=env, capture_output=True,
                                text=True, timeout=timeout)
         except subprocess.TimeoutExpired:
             return {"unavailable": f"timed out after {timeout} s at N={n}"}
@@ -119,7 +125,7 @@ def run_reference_cuda_build(n=8192, tile=32, gw=64, gh=64, timeout=300):
         rec = open(os.path.join(tmp, "csv", files[0])).read().strip().split(",")
     cuda_s, kernel_s, cublas_s = float(rec[6]), float(rec[7]), float(rec[8])
     fl = 2.0 * n ** 3 / 1e12
-    return {"N": n, "launch": f"{gw}x{gh} CTAs of {tile}x{tile} threads", "ranks": 1, "gpus": 1,
+    return {"N": n, "launch": f"{gw}x{gh} CTAs of {tile}x{tile} threads", "ranks": ranks, "gpus": ranks,
             "cuda_pass_tflops": fl / cuda_s if cuda_s > 0 else None, "cuda_pass_s": cuda_s,
             "gemm_kernel_tflops": fl / kernel_s if kernel_s > 0 else None, "gemm_kernel_s": kernel_s,
             "cublasxt_pass_tflops": fl / cublas_s if cublas_s > 0 else None, "cublasxt_pass_s": cublas_s,
@@ -557,9 +563,11 @@ def product_arm(args):
     int8_pk, int8_src = int8_peak()
 
     passes_on_c = [0]  # C += A*B passes accumulated in the device C blocks since s.fill() zeroed them
+    primary_summa = s
 
-    def measure(backend, warmup, steps, sample_clocks):
-        passes_on_c[0] += warmup + steps
+    def measure(backend, warmup, steps, sample_clocks, s=s):
+        if s is primary_summa:
+            passes_on_c[0] += warmup + steps
         for _ in range(warmup):
             s.run(backend, 0, sptr, stats=False)
         torch.cuda.synchronize()
@@ -682,6 +690,25 @@ def product_arm(args):
         cublas = {"value": cb["tflops"], "unit": UNIT, "ms_per_step": cb["ms"], "what": "same SUMMA loop, local GEMM = cublasDgemm (library call, not the product)"}
     s.destroy()
 
+    # ---------------- the north star's transport, measured with the same kernel: ncclBroadcast on row / column communicators ----------------
+    nccl = None
+    if world > 1 and not args.no_secondary:
+        saved = os.environ.get("PHPC_PANEL")
+        os.environ["PHPC_PANEL"] = "nccl"
+        try:
+            s2 = capi.Summa(comm, N, args.kc)
+            s2.fill(capi.FILL_SEEDED)
+            nb = measure(primary, 1, max(1, min(2, args.steps)), False, s=s2)
+            nccl = {"value": nb["tflops"], "unit": UNIT, "ms_per_step": nb["ms"], "exposed_frac": nb["exposed"],
+                    "what": "same device-resident SUMMA and local GEMM, panels moved by one ncclGroup of ncclBroadcast on the row and the column "
+                            "communicator (ncclCommSplit) per K chunk instead of the default copy-engine pulls over CUDA IPC (PHPC_PANEL=nccl)"}
+            s2.destroy()
+        finally:
+            if saved is None:
+                os.environ.pop("PHPC_PANEL", None)
+            else:
+                os.environ["PHPC_PANEL"] = saved
+
     # ---------------- e2e through the reference-facing C-ABI on host matrices ----------------
     e2e = None
     if not args.no_e2e:
@@ -703,6 +730,13 @@ def product_arm(args):
         cpu["reference_summa_all_cores"] = run_reference_summa_all_cores()
 
     ref_cuda = None
+    barrier()
+    if rank == 0 and world > 1 and not args.no_refcuda:
+        # the reference's own CUDA + MPI program on the same number of ranks = GPUs, sane launch grid
+        try:
+            ref_cuda = [run_reference_cuda_build(n=8192, gw=148, gh=4, ranks=world, timeout=420)]
+        except Exception as e:
+            ref_cuda = [{"unavailable": f"{type(e).__name__}: {e}"}]
     if rank == 0 and world == 1 and not args.no_refcuda:
         # the reference's build with (a) its default launch, one 32x32 CTA (what its own CSV sweeps use),
         # and (b) a sane launch, 148x4 CTAs
@@ -740,6 +774,7 @@ def product_arm(args):
             "local_gemm": names[primary],
             names[secondary]: other,
             "cublas_dgemm": cublas,
+            "nccl_broadcast_transport": nccl,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -147,6 +147,11 @@ def load():
     L.phpc_host_plan.restype = ctypes.c_int
     L.phpc_summa_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.phpc_summa_create.restype = ctypes.c_void_p
+    L.phpc_summa_create_mkn.argtypes = [ctypes.c_int] * 5
+    L.phpc_summa_create_mkn.restype = ctypes.c_void_p
+    L.phpc_summa_schedule_mkn.argtypes = [ctypes.c_int] * 8 + [ctypes.POINTER(SummaStep), ctypes.c_int, c_int_p, c_int_p]
+    L.phpc_summa_schedule_mkn.restype = ctypes.c_int
+    L.phpc_summa_global.argtypes = [ctypes.c_void_p, c_int_p]
     L.phpc_summa_destroy.argtypes = [ctypes.c_void_p]
     L.phpc_summa_upload.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, c_double_p]
     L.phpc_summa_fill.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_ulonglong]
@@ -270,6 +275,17 @@ def summa_schedule(N, r, c, pi, pj, kc=0):
     return list(steps), m.value, n.value
 
 
+def summa_schedule_mkn(M, K, N, r, c, pi, pj, kc=0):
+    L = load()
+    count = L.phpc_summa_schedule_mkn(M, K, N, r, c, pi, pj, kc, None, 0, None, None)
+    if count < 0:
+        raise ValueError("M, N must be divisible by the grid dimensions and K by their least common multiple")
+    steps = (SummaStep * count)()
+    m, n = ctypes.c_int(), ctypes.c_int()
+    L.phpc_summa_schedule_mkn(M, K, N, r, c, pi, pj, kc, steps, count, ctypes.byref(m), ctypes.byref(n))
+    return list(steps), m.value, n.value
+
+
 def ozaki_config():
     """The fixed arithmetic of the tcgen05 (Ozaki) path: digits per operand, int8 products per FP64 product, K chunk, guard spread."""
     v = [ctypes.c_int() for _ in range(4)]
@@ -328,10 +344,17 @@ def dims_create(size):
 class Summa:
     """Device-resident SUMMA object (phpc_summa_* additions of include/phpc_summa.h)."""
 
-    def __init__(self, grid_comm, n, kc=0):
+    def __init__(self, grid_comm, n, kc=0, m=None, k=None):
+        """n x n problem, or (m=, k=) given: C[m x n] += A[m x k] * B[k x n] (phpc_summa_create_mkn)."""
         self.L = load()
         self.n = n
-        self.h = self.L.phpc_summa_create(grid_comm, n, kc)
+        if m is None and k is None:
+            self.h = self.L.phpc_summa_create(grid_comm, n, kc)
+        else:
+            self.h = self.L.phpc_summa_create_mkn(grid_comm, n if m is None else m, n if k is None else k, n, kc)
+        g = (ctypes.c_int * 3)()
+        self.L.phpc_summa_global(self.h, g)
+        self.mkn = (g[0], g[1], g[2])
         d, co, bl = (ctypes.c_int * 2)(), (ctypes.c_int * 2)(), (ctypes.c_int * 2)()
         self.L.phpc_summa_geometry(self.h, d, co, bl)
         self.dims, self.coords, self.block = (d[0], d[1]), (co[0], co[1]), (bl[0], bl[1])

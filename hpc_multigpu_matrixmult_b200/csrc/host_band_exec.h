@@ -64,7 +64,8 @@ inline int host_plan(int m, int nsteps, int bands, int align, phpc_host_op *ops,
 
 /* The rank's blocks as the executor needs them (a 1 x 1 grid has pi = pj = 0, m = n = N; the fields are kept general). */
 struct BandGeom {
-  int N;           /* leading dimension of the FULL host matrices */
+  int N;           /* leading dimension of the FULL host matrices B and C (global columns) */
+  int lda_host = 0; /* leading dimension of the FULL host matrix A (global K); 0 = N (square problem) */
   int m, n;        /* the rank's C block */
   int pi, pj;      /* grid coordinates: the block starts at host row pi*m, column pj*n */
   long long ldn;   /* leading dimension of the B store and of the C block in HBM */
@@ -89,7 +90,7 @@ struct BandBackend {
 /* Walks the operation list; returns the number of GEMM kernels launched.  Does not synchronise. */
 inline int band_execute(const BandGeom &g, const phpc_host_op *ops, int nops, const double *hA, const double *hB, double *hC,
                         const BandBackend &be) {
-  const size_t N = (size_t)g.N;
+  const size_t N = (size_t)g.N, KA = (size_t)(g.lda_host > 0 ? g.lda_host : g.N);
   std::vector<void *> done(nops, nullptr);
   std::vector<char> needed(nops, 0);
   for (int i = 0; i < nops; ++i)
@@ -107,8 +108,8 @@ inline int band_execute(const BandGeom &g, const phpc_host_op *ops, int nops, co
       case PHPC_HOP_UPLOAD_A: {
         const phpc_summa_step &q = g.steps[o.step];
         const size_t ld = (size_t)band_pad_ld(q.width);
-        be.copy2d(be.self, o.stream, g.dA + q.a_off + (size_t)o.row0 * ld, ld * sizeof(double), hA + host_row * N + (size_t)q.k0,
-                  N * sizeof(double), (size_t)q.width * sizeof(double), (size_t)o.rows, 1);
+        be.copy2d(be.self, o.stream, g.dA + q.a_off + (size_t)o.row0 * ld, ld * sizeof(double), hA + host_row * KA + (size_t)q.k0,
+                  KA * sizeof(double), (size_t)q.width * sizeof(double), (size_t)o.rows, 1);
         break;
       }
       case PHPC_HOP_UPLOAD_B: {

@@ -59,11 +59,12 @@ static int env_int(const char *name, int dflt) {
 /* ------------------------------------------------------------------------- */
 /* schedule (pure host arithmetic)                                            */
 /* ------------------------------------------------------------------------- */
-extern "C" int phpc_summa_schedule(int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps, int *m_out,
-                                   int *n_out) {
-  if (N <= 0 || r <= 0 || c <= 0 || N % r || N % c) return -1;
+extern "C" int phpc_summa_schedule_mkn(int M, int K, int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps,
+                                       int *m_out, int *n_out) {
+  if (M <= 0 || K <= 0 || N <= 0 || r <= 0 || c <= 0 || M % r || N % c) return -1;
   const int lcm = r / gcd_int(r, c) * c;
-  const int m = N / r, n = N / c, pk = N / lcm; /* reference :36-39 */
+  if (K % lcm) return -1;
+  const int m = M / r, n = N / c, pk = K / lcm; /* reference :36-39 (square there: M = K = N) */
   if (kc <= 0 || kc > pk) kc = pk;
   if (m_out) *m_out = m;
   if (n_out) *n_out = n;
@@ -93,6 +94,12 @@ extern "C" int phpc_summa_schedule(int N, int r, int c, int pi, int pj, int kc, 
     }
   }
   return count;
+}
+
+extern "C" int phpc_summa_schedule(int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps, int *m_out,
+                                   int *n_out) {
+  if (N <= 0 || r <= 0 || c <= 0 || N % r || N % c) return -1; /* N % lcm == 0 follows */
+  return phpc_summa_schedule_mkn(N, N, N, r, c, pi, pj, kc, steps, max_steps, m_out, n_out);
 }
 
 /* Operation list of the band-pipelined host-sourced run on one GPU (phpc_host_op in phpc_summa.h): pure arithmetic,
@@ -155,7 +162,8 @@ static void nccl_grid_get(MPI_Comm grid_comm, int size, int rank, int r, int c, 
 struct phpc_summa {
   MPI_Comm grid_comm;
   int rank, size;
-  int N, r, c, pi, pj, lcm, m, n, pk, kc;
+  int N, r, c, pi, pj, lcm, m, n, pk, kc; /* N = global columns of B and C (= leading dimension of host B, C) */
+  int gM, gK;                             /* global rows of A and C, global K (= leading dimension of host A); square: all N */
   long long ldn;   /* padded leading dimension of B chunks and of C */
   long long lda_k; /* padded leading dimension of a full-width A chunk */
   std::vector<phpc_summa_step> steps;
@@ -165,6 +173,7 @@ struct phpc_summa {
   int nbuf = 0;
   double *ringA = nullptr, *ringB = nullptr; /* nbuf receive buffers each */
   double *gather_stage = nullptr;            /* rank 0: two C-block landing buffers for the gather */
+  double *dC0 = nullptr;                     /* multi-rank host-sourced runs: the caller's C block, uploaded under the loop and added at the end */
   /* panel transport: 0 = ncclBroadcast on row/column communicators, 1 = copy-engine pull from the
    * owner's store through CUDA IPC peer mappings (no SMs, no rendezvous) */
   int transport = 0;
@@ -191,7 +200,9 @@ static int pick_device(int rank) {
   return rank % count;
 }
 
-extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
+extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) { return phpc_summa_create_mkn(grid_comm, n, n, n, kc); }
+
+extern "C" phpc_summa *phpc_summa_create_mkn(MPI_Comm grid_comm, int gm, int gk, int n, int kc) {
   phpc_summa *s = new phpc_summa();
   s->grid_comm = grid_comm;
   int dims[2], periods[2], coords[2];
@@ -199,15 +210,18 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   MPI_Comm_size(grid_comm, &s->size);
   MPI_Cart_get(grid_comm, 2, dims, periods, coords);
   s->N = n;
+  s->gM = gm;
+  s->gK = gk;
   s->r = dims[0];
   s->c = dims[1];
   s->pi = coords[0];
   s->pj = coords[1];
-  PHPC_REQUIRE(n > 0 && n % s->r == 0 && n % s->c == 0, "matrix size must be divisible by the process grid dimensions");
   s->lcm = s->r / gcd_int(s->r, s->c) * s->c;
-  s->m = n / s->r;
+  PHPC_REQUIRE(n > 0 && gm > 0 && gk > 0 && gm % s->r == 0 && n % s->c == 0 && gk % s->lcm == 0,
+               "matrix size must be divisible by the process grid dimensions");
+  s->m = gm / s->r;
   s->n = n / s->c;
-  s->pk = n / s->lcm;
+  s->pk = gk / s->lcm;
   /* multi-rank default 8192 = the K chunk of the tcgen05 launcher: one set of exponent / split kernels and two C passes per
    * transferred chunk (4096 doubled both per flop); the ring buffers stay below 2 GiB per slot up to N = 65536 on 2 x 4 */
   if (kc <= 0) kc = env_int("PHPC_KC", s->size == 1 ? s->pk : 8192);
@@ -216,10 +230,10 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   s->ldn = phpc_pad_ld(s->n);
   s->lda_k = phpc_pad_ld(kc);
 
-  const int nsteps = phpc_summa_schedule(n, s->r, s->c, s->pi, s->pj, kc, nullptr, 0, nullptr, nullptr);
+  const int nsteps = phpc_summa_schedule_mkn(gm, gk, n, s->r, s->c, s->pi, s->pj, kc, nullptr, 0, nullptr, nullptr);
   PHPC_REQUIRE(nsteps > 0, "empty SUMMA schedule");
   s->steps.resize(nsteps);
-  phpc_summa_schedule(n, s->r, s->c, s->pi, s->pj, kc, s->steps.data(), nsteps, nullptr, nullptr);
+  phpc_summa_schedule_mkn(gm, gk, n, s->r, s->c, s->pi, s->pj, kc, s->steps.data(), nsteps, nullptr, nullptr);
 
   double t0 = now_s();
   phpc_b200_set_device(pick_device(s->rank));
@@ -263,12 +277,12 @@ extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) {
   {
     std::vector<phpc_summa_step> tmp(nsteps);
     for (int pj2 = 0; pj2 < s->c; ++pj2) {
-      phpc_summa_schedule(n, s->r, s->c, s->pi, pj2, kc, tmp.data(), nsteps, nullptr, nullptr);
+      phpc_summa_schedule_mkn(gm, gk, n, s->r, s->c, s->pi, pj2, kc, tmp.data(), nsteps, nullptr, nullptr);
       for (int q = 0; q < nsteps; ++q)
         if (tmp[q].own_a) s->root_a_off[q] = tmp[q].a_off;
     }
     for (int pi2 = 0; pi2 < s->r; ++pi2) {
-      phpc_summa_schedule(n, s->r, s->c, pi2, s->pj, kc, tmp.data(), nsteps, nullptr, nullptr);
+      phpc_summa_schedule_mkn(gm, gk, n, s->r, s->c, pi2, s->pj, kc, tmp.data(), nsteps, nullptr, nullptr);
       for (int q = 0; q < nsteps; ++q)
         if (tmp[q].own_b) s->root_b_off[q] = tmp[q].b_off;
     }
@@ -411,6 +425,7 @@ extern "C" void phpc_summa_destroy(phpc_summa *s) {
   if (s->ringA) cudaFree(s->ringA);
   if (s->ringB) cudaFree(s->ringB);
   if (s->gather_stage) cudaFree(s->gather_stage);
+  if (s->dC0) cudaFree(s->dC0);
   for (cudaEvent_t e : s->ev_bcast) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_free) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_g0) cudaEventDestroy(e);
@@ -426,6 +441,12 @@ extern "C" void phpc_summa_destroy(phpc_summa *s) {
   cudaEventDestroy(s->ev_user);
   delete s;
   PHPC_TRACE(rank_dbg, "destroy", t0);
+}
+
+extern "C" void phpc_summa_global(const phpc_summa *s, int mkn[3]) {
+  mkn[0] = s->gM;
+  mkn[1] = s->gK;
+  mkn[2] = s->N;
 }
 
 extern "C" void phpc_summa_geometry(const phpc_summa *s, int dims[2], int coords[2], int block[2]) {
@@ -445,11 +466,11 @@ extern "C" void phpc_summa_zero_c(phpc_summa *s) {
 /* owned chunks of step q out of FULL N x N host matrices: the windows reference :42-44 point into */
 static void upload_step(phpc_summa *s, int qi, const double *A, const double *B, cudaStream_t st) {
   const phpc_summa_step &q = s->steps[qi];
-  const size_t N = (size_t)s->N;
+  const size_t N = (size_t)s->N, K = (size_t)s->gK;
   if (q.own_a) {
-    const double *src = A + (size_t)s->pi * s->m * N + (size_t)q.k0;
+    const double *src = A + (size_t)s->pi * s->m * K + (size_t)q.k0;
     const size_t ld = phpc_pad_ld(q.width);
-    CUDA_CHECK(cudaMemcpy2DAsync(s->dA + q.a_off, ld * sizeof(double), src, N * sizeof(double), (size_t)q.width * sizeof(double), s->m,
+    CUDA_CHECK(cudaMemcpy2DAsync(s->dA + q.a_off, ld * sizeof(double), src, K * sizeof(double), (size_t)q.width * sizeof(double), s->m,
                                  cudaMemcpyHostToDevice, st));
   }
   if (q.own_b) {
@@ -482,12 +503,16 @@ extern "C" void phpc_summa_fill(phpc_summa *s, int kind, unsigned long long seed
   cudaStream_t st = s->ctx->compute;
   for (const phpc_summa_step &q : s->steps) {
     if (q.own_a)
-      phpc_fill_device(s->dA + q.a_off, phpc_pad_ld(q.width), s->m, q.width, (long long)s->pi * s->m, q.k0, s->N, kind, seed_a, st);
+      phpc_fill_device(s->dA + q.a_off, phpc_pad_ld(q.width), s->m, q.width, (long long)s->pi * s->m, q.k0, s->gK, kind, seed_a, st);
     if (q.own_b) phpc_fill_device(s->dB + q.b_off, s->ldn, q.width, s->n, q.k0, (long long)s->pj * s->n, s->N, kind, seed_b, st);
   }
   CUDA_CHECK(cudaMemsetAsync(s->dC, 0, s->c_elems * sizeof(double), st));
   CUDA_CHECK(cudaStreamSynchronize(st));
   if (s->size > 1) MPI_Barrier(s->grid_comm); /* every store is valid before anyone pulls from it */
+}
+
+__global__ void add_inplace_kernel(double *__restrict__ c, const double *__restrict__ c0, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c[i] += c0[i];
 }
 
 /* ------------------------------------------------------------------------- */
@@ -519,28 +544,39 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
   CUDA_CHECK(cudaStreamWaitEvent(comm, s->ev_begin, 0));
   const bool any_comm = (s->r > 1 || s->c > 1);
   const bool pull = any_comm && s->transport == 1;
+  bool late_c = false;
   cudaStream_t comm2 = ctx->comm2;
   if (pull) CUDA_CHECK(cudaStreamWaitEvent(comm2, s->ev_begin, 0));
   if (host_src) {
     CUDA_CHECK(cudaStreamWaitEvent(copy, s->ev_begin, 0));
     if (pull) {
-      /* Peers pull straight from this rank's store.  All uploads are enqueued now, in step order (step 0 first, then the C
-       * block, then the rest), each followed by an interprocess event; the host barrier only orders the ENQUEUE of those
+      /* Peers pull straight from this rank's store.  All uploads are enqueued now, in step order, each followed by an
+       * interprocess event; the host barrier only orders the ENQUEUE of those
        * records before the peers enqueue their waits - the copies themselves run under the GEMMs of earlier steps. */
       for (int q = 0; q < nsteps; ++q) {
         upload_step(s, q, hA, hB, copy);
         CUDA_CHECK(cudaEventRecord(s->ev_up[q], copy));
-        if (q == 0) {
-          upload_c(s, hC, copy);
-          CUDA_CHECK(cudaEventRecord(s->ev_cup, copy));
-        }
       }
+      /* The caller's C block must not hold up the first GEMM (it is as large as everything step 0 needs): the loop runs on a
+       * zeroed block, the caller's block follows the operands into a side buffer and is added once at the end
+       * (C0 + sum of the chunk products instead of ((C0 + P0) + P1) + ...: one rounding of difference at most). */
+      CUDA_CHECK(cudaMemsetAsync(s->dC, 0, s->c_elems * sizeof(double), comp));
+      if (hC) {
+        if (!s->dC0) CUDA_CHECK(cudaMalloc(&s->dC0, s->c_elems * sizeof(double)));
+        const size_t Nn = (size_t)s->N;
+        CUDA_CHECK(cudaMemcpy2DAsync(s->dC0, s->ldn * sizeof(double), hC + (size_t)s->pi * s->m * Nn + (size_t)s->pj * s->n, Nn * sizeof(double),
+                                     (size_t)s->n * sizeof(double), s->m, cudaMemcpyHostToDevice, copy));
+        if (s->ldn != s->n) /* the padding columns of the side buffer are added too: keep them defined */
+          CUDA_CHECK(cudaMemset2DAsync(s->dC0 + s->n, s->ldn * sizeof(double), 0, (size_t)(s->ldn - s->n) * sizeof(double), s->m, copy));
+      }
+      CUDA_CHECK(cudaEventRecord(s->ev_cup, copy));
+      late_c = hC != nullptr;
       MPI_Barrier(s->grid_comm);
     } else {
       upload_c(s, hC, copy);
       CUDA_CHECK(cudaEventRecord(s->ev_cup, copy));
     }
-    CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_cup, 0));
+    if (!late_c && !(pull)) CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_cup, 0));
   }
   /* stage-in of step q = upload of the owned chunks (host-sourced) + the panel transfers */
   auto stage_in = [&](int q) {
@@ -630,6 +666,11 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
     if (any_comm) CUDA_CHECK(cudaEventRecord(s->ev_free[slot], comp));
     /* prefetch: the stage-in of the next nbuf-1 steps runs under this GEMM */
     while (issued < nsteps && issued < q + s->nbuf) stage_in(issued++);
+  }
+  if (late_c) {
+    CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_cup, 0));
+    add_inplace_kernel<<<ctx->sm_count * 8, 256, 0, comp>>>(s->dC, s->dC0, s->c_elems);
+    CUDA_CHECK(cudaGetLastError());
   }
   CUDA_CHECK(cudaEventRecord(s->ev_end, comp));
   if (user_stream) CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)user_stream, s->ev_end, 0));
@@ -751,6 +792,7 @@ static void summa_run_host_banded(phpc_summa *s, int backend, int ctas, const do
   phpc::BandBackend be = {&cb, cb_copy2d, cb_record, cb_wait, cb_gemm};
   phpc::BandGeom g;
   g.N = s->N;
+  g.lda_host = s->gK;
   g.m = s->m;
   g.n = s->n;
   g.pi = s->pi;

@@ -12,12 +12,13 @@
  *   - C += A*B (the local GEMM accumulates, :93); after return rank 0 holds the
  *     full C, every other rank its own block at its global offset (:97-110);
  *   - *compute_time = device seconds of the local GEMMs summed over the steps (:94).
- * What changed underneath: the panels never touch host memory.  Each rank uploads
- * its owned blocks once, the k-loop runs on device with ncclBroadcast on per-row /
- * per-column NCCL communicators, multi-buffered on a communication stream so the
- * broadcast of step k+1.. overlaps the DMMA GEMM of step k, and the C block comes
- * back once at the end.  MPI (real or the single-node shim in mpi_shim/) is only
- * the control plane: bootstrap of the NCCL id, barriers, the final gather.
+ * What changed underneath: the panels never touch host memory.  Each rank uploads its owned blocks chunk by chunk under
+ * the GEMMs of earlier chunks, the k-loop runs on device: the K chunks a rank does not own are pulled straight out of the
+ * owner's HBM by the copy engines over NVLink (CUDA IPC; PHPC_PANEL=nccl uses one ncclGroup of ncclBroadcast on the
+ * per-row / per-column NCCL communicators instead), multi-buffered on communication streams so the transfer of chunk
+ * q+1.. overlaps the local GEMM of chunk q (the tcgen05 kernel of csrc/ozaki_gemm.cuh; PHPC_GEMM=dmma = native FP64),
+ * and the C block comes back once at the end.  MPI (real or the single-node shim in mpi_shim/) is only the control plane:
+ * NCCL id / IPC handle exchange, barriers, the optional MPI gather.
  */
 #ifndef _PHPC_SUMMA_H
 #define _PHPC_SUMMA_H
@@ -58,6 +59,9 @@ typedef struct phpc_summa_step {
  * max_steps entries, returns the number of steps (or -1 if N is not divisible by r
  * and c).  m/n/lda_pad/ldb_pad describe the rank's blocks (may be NULL). */
 int phpc_summa_schedule(int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps, int *m_out, int *n_out);
+/* The same for C[M x N] += A[M x K] * B[K x N]: blocks M/r x N/c, K panels of K/lcm(r,c) (-1 unless M % r == N % c == K % lcm == 0). */
+int phpc_summa_schedule_mkn(int M, int K, int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps, int *m_out,
+                            int *n_out);
 
 /* One operation of the band-pipelined host-sourced run on a 1 x 1 grid (phpc_summa_run_host): the rank's
  * C block is cut into row bands; band b is uploaded, multiplied over every K chunk and downloaded while
@@ -98,13 +102,20 @@ typedef struct phpc_summa phpc_summa; /* opaque: blocks in HBM + NCCL row/col co
 /* Collective over grid_comm.  Binds the rank to a GPU (PHPC_DEVICE, else
  * LOCAL_RANK, else rank % device_count), builds/caches the NCCL communicators and
  * allocates the rank's A, B, C blocks and the receive ring in HBM.  kc <= 0 picks
- * the default (whole panel on a 1x1 grid, 4096 otherwise; env PHPC_KC overrides).
+ * the default (whole panel on a 1x1 grid, 8192 otherwise; env PHPC_KC overrides).
  * Panel transport (env PHPC_PANEL): "nccl" = ncclBroadcast on the row / column
  * communicators; "pull" (default) = each rank copies the chunks it does not own
  * straight out of the owner's HBM with the copy engines over NVLink (CUDA IPC peer
  * mappings): same data movement as the broadcast, but no SMs and no rendezvous.
  * create / destroy / upload / fill / run_host are collective over grid_comm. */
 phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc);
+/* The same object for a general C[M x N] += A[M x K] * B[K x N] (the reference is square only, src/phpc_summa.c:36-39):
+ * M % r == 0, N % c == 0, K % lcm(r,c) == 0.  Rank (i,j) owns rows i*M/r.. of A and C, columns j*N/c.. of B and C, and the K
+ * panels of width K/lcm as in the square case.  Host matrices passed to upload / run_host / download_c are the FULL
+ * A (M x K, ld K), B (K x N, ld N), C (M x N, ld N).  phpc_summa_create(comm, n, kc) == phpc_summa_create_mkn(comm, n, n, n, kc). */
+phpc_summa *phpc_summa_create_mkn(MPI_Comm grid_comm, int m, int k, int n, int kc);
+/* Global problem size {M, K, N} of the object. */
+void phpc_summa_global(const phpc_summa *s, int mkn[3]);
 void phpc_summa_destroy(phpc_summa *s);
 /* Upload the rank's owned blocks from FULL host matrices (C may be NULL = zero). */
 void phpc_summa_upload(phpc_summa *s, const double *A, const double *B, const double *C);

@@ -12,7 +12,39 @@ sys.path.insert(0, ROOT)
 from hpc_multigpu_matrixmult_b200 import capi  # noqa: E402
 
 
+def rect(r, c, M, K, N, out, kc):
+    """General C[M x N] += A[M x K] * B[K x N] through the object API (phpc_summa_create_mkn): device-generated blocks, then
+    blocks uploaded from full host matrices (nonzero C), both with the default (tcgen05) local GEMM; gathered to rank 0."""
+    L = capi.load()
+    M_ = capi.mpi()
+    M_.MPI_Init(None, None)
+    rank = int(os.environ.get("PHPC_MPI_RANK", "0"))
+    comm = capi.cart_create((r, c))
+    s = capi.Summa(comm, N, kc, m=M, k=K)
+    assert s.mkn == (M, K, N) and s.block == (M // r, N // c)
+    s.fill(capi.FILL_SEEDED)
+    s.run()
+    Cd = np.zeros((M, N))
+    s.download_c(Cd, gather=True)
+    A = np.empty((M, K))
+    B = np.empty((K, N))
+    C0 = np.empty((M, N))
+    L.phpc_fill_host(capi._dp(A), K, M, K, 0, 0, K, capi.FILL_SEEDED, 91)
+    L.phpc_fill_host(capi._dp(B), N, K, N, 0, 0, N, capi.FILL_SEEDED, 92)
+    L.phpc_fill_host(capi._dp(C0), N, M, N, 0, 0, N, capi.FILL_SEEDED, 93)
+    Ch = C0.copy()
+    s.run_host(A, B, Ch)
+    s.destroy()
+    if rank == 0:
+        np.save(out, np.stack([Cd, Ch]))
+    M_.MPI_Finalize()
+
+
 def main():
+    if os.environ.get("PHPC_TEST_RECT"):
+        r, c = (int(x) for x in sys.argv[1].split("x"))
+        M, K, N = (int(x) for x in os.environ["PHPC_TEST_RECT"].split(","))
+        return rect(r, c, M, K, N, sys.argv[4], int(sys.argv[5]) if len(sys.argv) > 5 else 0)
     r, c = (int(x) for x in sys.argv[1].split("x"))
     N, fill, out = int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
     kc = int(sys.argv[5]) if len(sys.argv) > 5 else 0

@@ -140,3 +140,27 @@ def test_ozaki_config_is_fixed(capi, monkeypatch):
     assert capi.default_backend() == capi.BACKEND_OZAKI
     monkeypatch.setenv("PHPC_GEMM", "dmma")
     assert capi.default_backend() == capi.BACKEND_DMMA
+
+
+def test_rectangular_schedule_tiles_k_exactly_and_owners_follow_the_reference(capi):
+    """phpc_summa_schedule_mkn: K panels of K/lcm owned as in the reference (A panel k by column k % c, B panel k by row k % r,
+    src/phpc_summa.c:64-65), cut into chunks that tile [0, K) exactly on every rank; the square call is the M = K = N case."""
+    M, K, N = 600, 1080, 792
+    for (r, c) in ((1, 1), (1, 2), (2, 1), (2, 2), (2, 4), (4, 2), (2, 3)):
+        lcm = r * c // __import__("math").gcd(r, c)
+        for pi in range(r):
+            for pj in range(c):
+                steps, m, n = capi.summa_schedule_mkn(M, K, N, r, c, pi, pj, 100)
+                assert (m, n) == (M // r, N // c)
+                assert steps[0].k0 == 0 and all(steps[i].k0 + steps[i].width == steps[i + 1].k0 for i in range(len(steps) - 1))
+                assert steps[-1].k0 + steps[-1].width == K
+                for st in steps:
+                    assert st.panel == st.k0 // (K // lcm)
+                    assert (st.a_root, st.b_root) == (st.panel % c, st.panel % r)
+                    assert st.own_a == (st.a_root == pj) and st.own_b == (st.b_root == pi)
+                    assert (st.a_off >= 0) == bool(st.own_a) and (st.b_off >= 0) == bool(st.own_b)
+    sq, m, n = capi.summa_schedule(768, 2, 4, 1, 3, 100)
+    rq, m2, n2 = capi.summa_schedule_mkn(768, 768, 768, 2, 4, 1, 3, 100)
+    assert (m, n) == (m2, n2) and [(a.k0, a.width, a.a_off, a.b_off) for a in sq] == [(b.k0, b.width, b.a_off, b.b_off) for b in rq]
+    with pytest.raises(ValueError):
+        capi.summa_schedule_mkn(600, 1081, 792, 2, 4, 0, 0)

@@ -149,6 +149,49 @@ def test_summa_chunked_k_loop_device_resident(gpu, capi, oracle):
         s.destroy()
 
 
+def test_rectangular_summa_object_single_rank(gpu, capi, oracle):
+    """SURVEY 8(f1) on one GPU: C[M x N] += A[M x K] * B[K x N] with M, K, N all different through phpc_summa_create_mkn: blocks
+    generated in HBM, blocks uploaded from full host matrices (chunk loop and row bands, nonzero C), every backend."""
+    import os
+
+    M, K, N = 700, 1100, 450
+    comm = capi.cart_create((1, 1))
+    A = oracle.fill(M, K, N=K, kind=1, seed=oracle.SEED_A)
+    B = oracle.fill(K, N, N=N, kind=1, seed=oracle.SEED_B)
+    want = oracle.gemm_block(A, B)
+    s = capi.Summa(comm, N, 300, m=M, k=K)
+    assert s.mkn == (M, K, N) and s.block == (M, N)
+    s.fill(capi.FILL_SEEDED)
+    for backend in (capi.BACKEND_OZAKI, capi.BACKEND_DMMA, capi.BACKEND_CUBLAS):
+        s.zero_c()
+        st = s.run(backend)
+        assert st.steps == 4
+        assert oracle.rel_frobenius(s.read_c_block(), want) <= 1e-14
+    C0 = oracle.fill(M, N, N=N, kind=1, seed=5)
+    saved = os.environ.get("PHPC_HOST_BANDS")
+    try:
+        for bands in ("1", "3"):
+            os.environ["PHPC_HOST_BANDS"] = bands
+            C = C0.copy()
+            s.run_host(A, B, C)
+            assert oracle.rel_frobenius(C, oracle.gemm_block(A, B, C0)) <= 1e-14, bands
+    finally:
+        if saved is None:
+            os.environ.pop("PHPC_HOST_BANDS", None)
+        else:
+            os.environ["PHPC_HOST_BANDS"] = saved
+    s.destroy()
+    # the reference's fill on a rectangular problem: A[i][j] = i*K + j, B[i][j] = i*N + j, exact while sums stay below 2^53
+    M, K, N = 96, 160, 224
+    s = capi.Summa(comm, N, 0, m=M, k=K)
+    s.fill(capi.FILL_INDEX)
+    s.run()
+    Ai = oracle.fill(M, K, N=K, kind=0)
+    Bi = oracle.fill(K, N, N=N, kind=0)
+    assert np.array_equal(s.read_c_block(), oracle.gemm_block(Ai, Bi))
+    s.destroy()
+
+
 def _device_gemm(capi, lib, n, kind, scale=1.0, cublas=False):
     """C = (scale*A) * B for the N x N synthetic matrices, all in HBM; returns device pointer of C."""
     ld = n

@@ -56,6 +56,23 @@ def test_summa_bit_exact_on_reference_fill(gpu, oracle, tmp_path, grid, ngpu):
         assert np.array_equal(C, exact)
 
 
+@pytest.mark.parametrize("grid,ngpu", [((1, 2), 2), ((2, 1), 2), ((2, 2), 4), ((2, 4), 8)])
+def test_rectangular_summa_object_api(gpu, oracle, tmp_path, grid, ngpu):
+    """general C[M x N] += A[M x K] * B[K x N] behind the device-resident object API (the reference is square
+    only, src/phpc_summa.c:36-39).  M, K, N all different, none a multiple of the 128 tile per block; device-generated blocks
+    and host-uploaded blocks with a nonzero C, against the oracle's block GEMM on the regenerated full matrices."""
+    _need(gpu, ngpu)
+    M, K, N = 2 * 4 * 75, 8 * 135, 4 * 2 * 99  # divisible by every grid dimension and lcm used here
+    Cs, _ = _run(grid, N, 1, tmp_path, kc=100, env={"PHPC_TEST_RECT": f"{M},{K},{N}"})
+    A = oracle.fill(M, K, N=K, kind=1, seed=oracle.SEED_A)
+    B = oracle.fill(K, N, N=N, kind=1, seed=oracle.SEED_B)
+    assert oracle.rel_frobenius(Cs[0], oracle.gemm_block(A, B)) <= 1e-14
+    A2 = oracle.fill(M, K, N=K, kind=1, seed=91)
+    B2 = oracle.fill(K, N, N=N, kind=1, seed=92)
+    C0 = oracle.fill(M, N, N=N, kind=1, seed=93)
+    assert oracle.rel_frobenius(Cs[1], oracle.gemm_block(A2, B2, C0)) <= 1e-14
+
+
 def test_golden_reference_summa_fixture(gpu, oracle, tmp_path):
     """The committed outputs of the reference's own SUMMA (4 ranks -> 2x2, N=48)."""
     _need(gpu, 4)
