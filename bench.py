@@ -660,16 +660,16 @@ def product_arm(args):
     # the multi-GPU parity check that runs with every bench line)
     m_blk, n_blk = s.block
     pi, pj = s.coords
-    pairs = sample_positions(pi * m_blk, m_blk, pj * n_blk, n_blk, 4242 + rank, 8)
+    vpos = sample_positions(pi * m_blk, m_blk, pj * n_blk, n_blk, 4242 + rank, 8)
     got = {}
-    for i in sorted({i for i, _ in pairs}):
+    for i in sorted({i for i, _ in vpos}):
         row = s.read_c_block(i - pi * m_blk, 0, 1, n_blk)[0]
-        for (i2, j) in pairs:
+        for (i2, j) in vpos:
             if i2 == i:
                 got[(i, j)] = row[j - pj * n_blk]
-    v_ok, v_worst = sampled_check(capi, L, N, pairs, got, passes_on_c[0])
+    v_ok, v_worst = sampled_check(capi, L, N, vpos, got, passes_on_c[0])
     value_verified = max_over_ranks(0.0 if v_ok else 1.0) == 0.0
-    value_verify = {"elements_checked_per_rank": len(pairs), "ranks": world, "worst_error_over_bound": max_over_ranks(v_worst),
+    value_verify = {"elements_checked_per_rank": len(vpos), "ranks": world, "worst_error_over_bound": max_over_ranks(v_worst),
                     "passes_accumulated": passes_on_c[0],
                     "how": "after the timed steps every rank reads sampled elements of its device C block (first/last row and column of the block + "
                            "random ones) and compares them with passes x the exactly summed FP64 dot product of the regenerated row of A and "

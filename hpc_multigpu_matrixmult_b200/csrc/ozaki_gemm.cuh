@@ -13,7 +13,7 @@
  * the row/column scale and balanced digits keep their sign, so what is dropped still cancels.
  * 28 int8 MMAs stand for one FP64 MMA.  The reference kernel this replaces is gemm_kernel of
  * src/phpc_gemm.cu:6-57 (same C += A.B contract); the arithmetic differs from it only in the
- * order of exact partial sums and in the two FP64 additions per K chunk.
+ * order of exact partial sums and in the two FP64 roundings per K chunk (joining the two passes, adding to C).
  *
  * Kernel (one CTA per SM, persistent over 128 x 128 output tiles, static round robin):
  *   K-outer schedule  per 32-byte k step ALL needed digit tiles of A and B are staged once (one
@@ -38,14 +38,18 @@
  *               tiles of 416 us) and the panels are then fetched from DRAM again and again (623 GB for a
  *               32768 x 8192 x 32768 launch).  The producers therefore start every tile together: one
  *               atomic counter per wave (all CTAs are resident: grid <= SM count, one CTA per SM).
- *   warp 0      producer: two cp.async.bulk copies per k step into a 3-stage mbarrier ring
+ *   warp 0      producer: two cp.async.bulk copies per k step into a 4-stage mbarrier ring (4 x 56 KiB)
  *   warp 1      TMEM allocator + MMA issuer: the whole warp walks warp-uniform, fully unrolled code
  *               and one elected lane issues tcgen05.mma.kind::i8 / tcgen05.commit (with the loops inside
  *               `if (lane == 0)` every MMA cost 140-180 cycles of register -> uniform register moves
  *               instead of 65; tools/umma_rate.cu, profiles/umma_rate*_r01.jsonl)
- *   warps 2-5   epilogue: tcgen05.ld the int32 accumulators of a pass, combine them exactly in
- *               FP64 (<= 53 significant bits), transpose through shared memory, one coalesced
- *               read-modify-write of C per pass with 32 loads in flight per lane
+ *   warps 4-11  epilogue (two warpgroups; setmaxnreg moves registers from warps 0-3 to them): thread = one tile row x 64
+ *               columns.  After each pass the int32 accumulators are combined exactly in FP64 into 64 registers per
+ *               thread (tcgen05.ld) and TMEM is handed back to the MMA warp at once; after pass 2 the two partial
+ *               results are joined with one rounding and C gets ONE read-modify-write per element and K chunk
+ *               (32-byte accesses, each thread owns 512 contiguous bytes of its row) while the MMA warp is already
+ *               working on the next tile: no accumulator double buffering needed, and half the C traffic of a
+ *               per-pass update
  *   guard       *p.guard != 0 (set by the exponent kernels: non-finite input, exponents near the FP64
  *               range limits, rows/columns spanning more than MAX_SPREAD binary orders of magnitude)
  *               makes the kernel return at once; the native-FP64 DMMA kernel launched right after it
@@ -80,10 +84,11 @@ constexpr int BKB = 32;                /* bytes of k per step = one int8 MMA (K 
 constexpr int SLOT_BYTES = BM * BKB;   /* one digit tile: 128 rows x 32 B */
 constexpr int TILE_BYTES = SLOT_BYTES;
 constexpr int STAGE_BYTES = 2 * S * SLOT_BYTES; /* A digit slots then B digit slots: 56 KiB */
-constexpr int STAGES = 3;
-constexpr int THREADS = 192;           /* warp 0 producer, warp 1 MMA, warps 2-5 epilogue */
-constexpr int EPI_WARP_BYTES = 32 * 33 * 8; /* per epilogue warp: 32 x 32 doubles, padded */
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 4 * EPI_WARP_BYTES;
+constexpr int STAGES = 4;
+constexpr int THREADS = 384;           /* warpgroup 0: warp 0 producer, warp 1 MMA issuer (warps 2, 3 idle); warpgroups 1-2: 8 epilogue warps */
+constexpr int EPI_WARPS = 8;
+constexpr int CTRL_REGS = 40, EPI_REGS = 232; /* setmaxnreg: the epilogue threads each hold 64 FP64 partial results across a pass */
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 constexpr int GROUPS_PER_PASS = 4;
 constexpr int NPASS = 2;
 constexpr int TMEM_COLS = GROUPS_PER_PASS * BN; /* 512 */
@@ -149,6 +154,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, int (&v)[32])
         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
         "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
         "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, int (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -265,54 +279,82 @@ __device__ __forceinline__ void mma_pass(const Params &p, uint32_t tmem_base, ui
   __syncwarp();
 }
 
-/* epilogue of one pass of one tile (one of the four epilogue warps = 32 rows): C += 2^(eA+eB-..) * sum_g 256^(G_HI-g) P_g */
+/* Epilogue, part 1 (per pass): drain the accumulators of pass PS into registers.  Thread = one row of the tile (TMEM lane) and
+ * 64 of its 128 columns; part[j] = sum_g 256^(G_HI-g) P_g exactly (|sum| < 2^53); pass 1 (groups 8..5) starts acc, pass 2
+ * (groups 4..2, weight 2^32 above it) is added with ONE rounding: acc = fl(part2 * 2^32 + part1).  The accumulators are handed
+ * back to the MMA warp as soon as the loads have completed, i.e. before anything touches global memory. */
 template <int PS>
-__device__ __forceinline__ void epilogue_pass(const Params &p, uint32_t tmem_base, uint32_t tfull, uint32_t tempty, uint32_t unit, uint32_t tr,
-                                              int quarter, int lane, int tn, int row0, int rows_here, int ea) {
+__device__ __forceinline__ void epilogue_collect(uint32_t tmem_base, uint32_t tfull, uint32_t tempty, uint32_t unit, int quarter, int half, int lane,
+                                                 double (&acc)[64]) {
   constexpr int G_HI = Pass<PS>::G_HI, G_LO = Pass<PS>::G_LO;
-  constexpr int SCALE = -2 * BAL_BITS + DIGIT_BITS * (2 * S - G_HI); /* weight of group G_HI relative to 2^(eA+eB) */
   mbar_wait(tfull, unit & 1);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    if (tn * BN + c0 >= p.N || rows_here <= 0) break;
-    double acc[32];
+  const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    double part[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) part[j] = 0.0;
 #pragma unroll
     for (int g = G_HI; g >= G_LO; --g) {
-      int v[32];
-      tmem_ld_32x32b_x32(tlane + (uint32_t)(g - G_LO) * BN + c0, v);
+      int v[16];
+      tmem_ld_32x32b_x16(tlane + (uint32_t)(g - G_LO) * BN + c0, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const double w = pow2d(DIGIT_BITS * (G_HI - g));
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = fma((double)v[j], w, acc[j]); /* exact: |sum| < 2^53 */
+      for (int j = 0; j < 16; ++j) part[j] = fma((double)v[j], w, part[j]); /* exact */
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) asm volatile("st.shared.f64 [%0], %1;" ::"r"(tr + (uint32_t)(lane * 33 + j) * 8), "d"(acc[j]) : "memory");
-    __syncwarp();
-    const int col = tn * BN + c0 + lane;
-    const int eb = (col < p.N) ? __ldg(p.eB + col) : ZERO_EXP;
-    double *cptr = p.C + (long long)row0 * p.ldc + col;
-    const bool col_ok = eb != ZERO_EXP && !(p.flags & 1);
-    /* all 32 row loads of this lane's column are issued before any is used: one memory
-     * round trip per 32x32 block instead of four */
-    double cold[32];
-#pragma unroll
-    for (int rr = 0; rr < 32; ++rr) cold[rr] = (col_ok && rr < rows_here) ? cptr[(long long)rr * p.ldc] : 0.0;
-#pragma unroll
-    for (int rr = 0; rr < 32; ++rr) {
-      double x;
-      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(tr + (uint32_t)(rr * 33 + lane) * 8) : "memory");
-      const int er = __shfl_sync(0xffffffffu, ea, rr);
-      if (col_ok && rr < rows_here && er != ZERO_EXP && x != 0.0) cptr[(long long)rr * p.ldc] = cold[rr] + x * pow2d(er + eb + SCALE);
-    }
-    __syncwarp();
+    for (int j = 0; j < 16; ++j) acc[c0 + j] = (PS == 0) ? part[j] : fma(part[j], pow2d(DIGIT_BITS * GROUPS_PER_PASS), acc[c0 + j]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncwarp();
   if (lane == 0) mbar_arrive(tempty);
+}
+
+/* Epilogue, part 2 (per tile): C[row][col0 .. col0+63] += acc * 2^(eA[row] + eB[col] - 60), one read-modify-write of C per K
+ * chunk.  Every thread owns 512 contiguous bytes of its row and moves them with 32-byte accesses (whole sectors); this runs
+ * while the MMA warp is already working on the next tile. */
+__device__ __forceinline__ void epilogue_update(const Params &p, const double (&acc)[64], int row, int col0, int ea) {
+  constexpr int SCALE = -2 * BAL_BITS + DIGIT_BITS * (2 * S - Pass<0>::G_HI); /* weight of group 8 relative to 2^(eA+eB) */
+  if (row >= p.M || ea == ZERO_EXP || (p.flags & 1)) return;
+  double *crow = p.C + (long long)row * p.ldc;
+  const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 31) == 0);
+#pragma unroll
+  for (int j0 = 0; j0 < 64; j0 += 16) { /* 4 x 32 bytes in flight per thread */
+    double c[16];
+    int eb[16];
+    bool vec[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int col = col0 + j0 + 4 * q;
+      vec[q] = vec_ok && col + 3 < p.N;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) eb[4 * q + e] = (col + e < p.N) ? __ldg(p.eB + col + e) : ZERO_EXP;
+      if (vec[q]) {
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c[4 * q]), "=d"(c[4 * q + 1]), "=d"(c[4 * q + 2]), "=d"(c[4 * q + 3]) : "l"(crow + col) : "memory");
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[4 * q + e] = (col + e < p.N) ? crow[col + e] : 0.0;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int col = col0 + j0 + 4 * q;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double x = acc[j0 + 4 * q + e];
+        if (x != 0.0 && eb[4 * q + e] != ZERO_EXP) c[4 * q + e] += x * pow2d(ea + eb[4 * q + e] + SCALE);
+      }
+      if (vec[q]) {
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(crow + col), "d"(c[4 * q]), "d"(c[4 * q + 1]), "d"(c[4 * q + 2]), "d"(c[4 * q + 3]) : "memory");
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (col + e < p.N && acc[j0 + 4 * q + e] != 0.0 && eb[4 * q + e] != ZERO_EXP) crow[col + e] = c[4 * q + e];
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) {
@@ -323,7 +365,6 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
   const uint32_t full0 = bars, empty0 = bars + 8 * STAGES;
   const uint32_t tfull = bars + 16 * STAGES, tempty = tfull + 8;
   const uint32_t tmem_slot = tempty + 8;
-  const uint32_t epi0 = bars + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -335,7 +376,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
       mbar_init(empty0 + 8 * s, 1);
     }
     mbar_init(tfull, 1);
-    mbar_init(tempty, 4);
+    mbar_init(tempty, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -349,58 +390,63 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  if (warp == 0) {
-    /* ===== producer: two contiguous bulk copies per k step ===== */
-    if (lane == 0 && !(p.flags & 2)) {
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CTRL_REGS));
+    if (warp == 0) {
+      /* ===== producer: two contiguous bulk copies per k step ===== */
+      if (lane == 0 && !(p.flags & 2)) {
+        int stage = 0;
+        uint32_t phase = 0;
+        constexpr size_t step_bytes = (size_t)S * TILE_BYTES;
+        int wave = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++wave) {
+          int tm, tn;
+          tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+          const int8_t *ta = p.TA + (size_t)tm * p.ksteps * step_bytes;
+          const int8_t *tb = p.TB + (size_t)tn * p.ksteps * step_bytes;
+          if (p.tstamp) p.tstamp[2 * (size_t)tile] = globaltimer_ns();
+          if (!(p.flags & 4)) {
+            /* all CTAs of this wave start streaming their panels together (every CTA is resident: grid <= SM count) */
+            unsigned int *ctr = p.wave_sync + wave;
+            const unsigned int expect = (unsigned int)min((long long)gridDim.x, (long long)total_tiles - (long long)wave * gridDim.x);
+            atomicAdd(ctr, 1u);
+            unsigned int seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+            } while (seen < expect);
+          }
+          load_pass<0>(p, ta, tb, smem_base, full0, empty0, stage, phase);
+          load_pass<1>(p, ta, tb, smem_base, full0, empty0, stage, phase);
+        }
+      }
+    } else if (warp == 1) {
+      /* ===== MMA issuer: the whole warp walks the loops (uniform control flow and addresses), one
+       * elected lane issues tcgen05.mma / tcgen05.commit ===== */
       int stage = 0;
       uint32_t phase = 0;
-      constexpr size_t step_bytes = (size_t)S * TILE_BYTES;
-      int wave = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++wave) {
-        int tm, tn;
-        tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-        const int8_t *ta = p.TA + (size_t)tm * p.ksteps * step_bytes;
-        const int8_t *tb = p.TB + (size_t)tn * p.ksteps * step_bytes;
-        if (p.tstamp) p.tstamp[2 * (size_t)tile] = globaltimer_ns();
-        if (!(p.flags & 4)) {
-          /* all CTAs of this wave start streaming their panels together (every CTA is resident: grid <= SM count) */
-          unsigned int *ctr = p.wave_sync + wave;
-          const unsigned int expect = (unsigned int)min((long long)gridDim.x, (long long)total_tiles - (long long)wave * gridDim.x);
-          atomicAdd(ctr, 1u);
-          unsigned int seen;
-          do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-          } while (seen < expect);
-        }
-        load_pass<0>(p, ta, tb, smem_base, full0, empty0, stage, phase);
-        load_pass<1>(p, ta, tb, smem_base, full0, empty0, stage, phase);
+      uint32_t unit = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mma_pass<0>(p, tmem_base, smem_base, full0, empty0, tfull, tempty, unit++, stage, phase);
+        mma_pass<1>(p, tmem_base, smem_base, full0, empty0, tfull, tempty, unit++, stage, phase);
       }
     }
-  } else if (warp == 1) {
-    /* ===== MMA issuer: the whole warp walks the loops (uniform control flow and addresses), one
-     * elected lane issues tcgen05.mma / tcgen05.commit ===== */
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t unit = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      mma_pass<0>(p, tmem_base, smem_base, full0, empty0, tfull, tempty, unit++, stage, phase);
-      mma_pass<1>(p, tmem_base, smem_base, full0, empty0, tfull, tempty, unit++, stage, phase);
-    }
   } else {
-    /* ===== epilogue: combine the groups of a pass exactly, then one C += per element ===== */
-    const int quarter = warp & 3;
-    const uint32_t tr = epi0 + (uint32_t)(warp - 2) * EPI_WARP_BYTES;
+    /* ===== epilogue (8 warps): drain both passes into registers, then ONE C += per element and K chunk ===== */
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
+    const int ew = warp - 4;
+    const int quarter = warp & 3; /* the TMEM lanes a warp may read: 32 * (warp id % 4) */
+    const int half = ew >> 2;     /* columns 0..63 or 64..127 of the tile */
     uint32_t unit = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int tm, tn;
       tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
-      const int row0 = tm * BM + quarter * 32;
-      const int my_row = row0 + lane;
-      const int ea = (my_row < p.M) ? p.eA[my_row] : ZERO_EXP;
-      const int rows_here = min(32, p.M - row0);
-      epilogue_pass<0>(p, tmem_base, tfull, tempty, unit++, tr, quarter, lane, tn, row0, rows_here, ea);
-      epilogue_pass<1>(p, tmem_base, tfull, tempty, unit++, tr, quarter, lane, tn, row0, rows_here, ea);
-      if (p.tstamp && warp == 2 && lane == 0) p.tstamp[2 * (size_t)tile + 1] = globaltimer_ns();
+      const int row = tm * BM + quarter * 32 + lane;
+      const int ea = (row < p.M) ? p.eA[row] : ZERO_EXP;
+      double acc[64];
+      epilogue_collect<0>(tmem_base, tfull, tempty, unit++, quarter, half, lane, acc);
+      epilogue_collect<1>(tmem_base, tfull, tempty, unit++, quarter, half, lane, acc);
+      epilogue_update(p, acc, row, tn * BN + half * 64, ea);
+      if (p.tstamp && ew == 0 && lane == 0) p.tstamp[2 * (size_t)tile + 1] = globaltimer_ns();
     }
   }
 

@@ -7,12 +7,12 @@ without any tensor core:
   split    e = 1 + floor(log2(max |x|)) per row of A / column of B of a K chunk (8192);
            q = rint(x * 2^(54-e)); q = sum_t d_t 256^(7-t) with balanced digits d_t in [-128, 127]
   products P_g = sum_{t+u=g} A_t @ B_u  in exact integers (int32 on the GPU), groups g = 2 .. 8
-  combine  per K chunk, pass 1 (groups 8..5) then pass 2 (groups 4..2):
-           v = sum_g P_g * 256^(g_hi-g)   (exact, < 2^53)
-           C = fl( C + v * 2^(eA[i] + eB[j] - 108 + 8*(14-g_hi)) )      (one rounding per pass)
+  combine  per K chunk, pass 1 (groups 8..5) and pass 2 (groups 4..2):
+           v_p = sum_g P_g * 256^(g_hi-g)        (exact, < 2^53)
+           x   = fl( v_2 * 2^32 + v_1 )          (first rounding: joining the two passes)
+           C   = fl( C + x * 2^(eA[i] + eB[j] - 60) )                     (second rounding)
 gemm_kernel() does exactly that with Python integers, so it reproduces the kernel's result including
-the order of its (two per chunk) floating-point roundings; gemm_balanced() adds all groups of a chunk
-with a single rounding (the ideal the two-pass kernel is compared with).  There is no reference
+its two floating-point roundings per chunk; gemm_balanced() is the same sum written as one expression.  There is no reference
 counterpart: the reference computes in native FP64 (src/phpc_gemm.cu:50-55); the model exists to pin
 the emulation algorithm itself, next to the oracle that pins the result.
 """
@@ -81,8 +81,8 @@ def gemm_balanced(a, b, c0=None, S=7, kc_max=8192, bits=54):
 
 
 def gemm_kernel(a, b, c0=None):
-    """C = c0 + a @ b exactly as csrc/ozaki_gemm.cuh computes it: per K chunk two passes of up to four groups, one FP64
-    addition into C per pass (pass 1 = groups 8..5, pass 2 = groups 4..2)."""
+    """C = c0 + a @ b exactly as csrc/ozaki_gemm.cuh computes it: per K chunk two passes of up to four groups (pass 1 = groups
+    8..5, pass 2 = groups 4..2), joined with one rounding, then one FP64 addition into C."""
     S, bits = S_DIGITS, BAL_BITS
     m, k = a.shape
     n = b.shape[1]
@@ -98,18 +98,23 @@ def gemm_kernel(a, b, c0=None):
                 acc = acc + (da[t - 1].astype(object) @ db[g - t - 1].astype(object))
             assert max(abs(int(v)) for v in acc.ravel()) < (1 << 31)  # fits the int32 TMEM accumulator
             groups[g] = acc
+        parts = []
         for ps in range(2):
             g_hi = S + 1 - GROUPS_PER_PASS * ps
             g_lo = max(2, g_hi - GROUPS_PER_PASS + 1)
             v = np.zeros((m, n), dtype=object)
             for g in range(g_lo, g_hi + 1):
                 v = v + groups[g] * (1 << (DIGIT_BITS * (g_hi - g)))
-            scale = -2 * bits + DIGIT_BITS * (2 * S - g_hi)
-            for i in range(m):
-                if ea[i] is None:
+            assert max(abs(int(x)) for x in v.ravel()) < (1 << 53)  # each pass is exact in FP64
+            parts.append(v)
+        # the kernel joins the passes with one rounding, fl(part2 * 2^32 + part1), then adds fl(C + x * 2^(eA + eB - 60))
+        total = parts[1] * (1 << (DIGIT_BITS * GROUPS_PER_PASS)) + parts[0]
+        scale = -2 * bits + DIGIT_BITS * (2 * S - (S + 1))
+        for i in range(m):
+            if ea[i] is None:
+                continue
+            for j in range(n):
+                if eb[j] is None or total[i, j] == 0:
                     continue
-                for j in range(n):
-                    if eb[j] is None or v[i, j] == 0:
-                        continue
-                    c[i, j] = c[i, j] + math.ldexp(float(v[i, j]), ea[i] + eb[j] + scale)
+                c[i, j] = c[i, j] + math.ldexp(float(total[i, j]), ea[i] + eb[j] + scale)
     return c
