@@ -677,7 +677,7 @@ def product_arm(args):
     launches_per_step = st.launches
     bytes_rx = st.bytes_received
     steps_per_summa = st.steps
-    kc_used = int(N / st.steps)
+    kc_used = getattr(s, "kc", int(N / st.steps))
     other = None
     if not args.no_secondary:
         sec = measure(secondary, 1, max(1, min(2, args.steps)), False)
@@ -759,7 +759,8 @@ def product_arm(args):
                                       "model (rel. Frobenius difference to native FP64 ~1e-15); chunks with Inf/NaN, near-range exponents or > 2^40 "
                                       "spread inside a row / column run on the native-FP64 DMMA kernel")
                        if primary == capi.BACKEND_OZAKI else "native FP64 DMMA",
-                       "N": N, "process_grid": f"{dims[0]}x{dims[1]}", "k_chunk": kc_used, "summa_steps": steps_per_summa,
+                       "N": N, "process_grid": f"{dims[0]}x{dims[1]}", "k_chunk": kc_used, "k_chunk_first": getattr(s, "kc_first", 0),
+                       "summa_steps": steps_per_summa,
                        "cache": "inputs_larger_than_l2 (operands are GiBs; L2 is 126 MB)", "exposed_broadcast_frac": exposed_frac,
                        "nvlink_bytes_received_rank0_per_step": bytes_rx},
             "value_verified": value_verified,

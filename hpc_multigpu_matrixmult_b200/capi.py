@@ -152,6 +152,7 @@ def load():
     L.phpc_summa_schedule_mkn.argtypes = [ctypes.c_int] * 8 + [ctypes.POINTER(SummaStep), ctypes.c_int, c_int_p, c_int_p]
     L.phpc_summa_schedule_mkn.restype = ctypes.c_int
     L.phpc_summa_global.argtypes = [ctypes.c_void_p, c_int_p]
+    L.phpc_summa_chunks.argtypes = [ctypes.c_void_p, c_int_p, c_int_p, c_int_p]
     L.phpc_summa_destroy.argtypes = [ctypes.c_void_p]
     L.phpc_summa_upload.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, c_double_p]
     L.phpc_summa_fill.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_ulonglong]
@@ -355,6 +356,9 @@ class Summa:
         g = (ctypes.c_int * 3)()
         self.L.phpc_summa_global(self.h, g)
         self.mkn = (g[0], g[1], g[2])
+        kc_, kf_, ns_ = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self.L.phpc_summa_chunks(self.h, ctypes.byref(kc_), ctypes.byref(kf_), ctypes.byref(ns_))
+        self.kc, self.kc_first, self.nsteps = kc_.value, kf_.value, ns_.value
         d, co, bl = (ctypes.c_int * 2)(), (ctypes.c_int * 2)(), (ctypes.c_int * 2)()
         self.L.phpc_summa_geometry(self.h, d, co, bl)
         self.dims, self.coords, self.block = (d[0], d[1]), (co[0], co[1]), (bl[0], bl[1])

@@ -55,7 +55,8 @@
  *               makes the kernel return at once; the native-FP64 DMMA kernel launched right after it
  *               with the opposite predicate computes that K chunk instead (phpc_launch_ozaki).
  * Earlier variants (pair-outer 128x256 tiles with TMA; K-outer with 16 TMA boxes per step; truncated
- * 7-bit digits, 36 products; a 2-CTA cta_group::2 kernel) and what was measured on them are in
+ * 7-bit digits, 36 products; a 2-CTA cta_group::2 kernel; clusters of two CTAs with the A digits multicast: same speed,
+ * profiles/ozaki_knobs_pair_multicast_r02.jsonl) and what was measured on them are in
  * profiles/ozaki_experiments_r01.md, profiles/ozaki_variants_r02.jsonl and profiles/ozaki_knobs_r02.jsonl.
  */
 #pragma once
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
+  const int worker = (int)blockIdx.x, workers = (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
         uint32_t phase = 0;
         constexpr size_t step_bytes = (size_t)S * TILE_BYTES;
         int wave = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++wave) {
+        for (int tile = worker; tile < total_tiles; tile += workers, ++wave) {
           int tm, tn;
           tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
           const int8_t *ta = p.TA + (size_t)tm * p.ksteps * step_bytes;
@@ -408,7 +410,8 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
           if (!(p.flags & 4)) {
             /* all CTAs of this wave start streaming their panels together (every CTA is resident: grid <= SM count) */
             unsigned int *ctr = p.wave_sync + wave;
-            const unsigned int expect = (unsigned int)min((long long)gridDim.x, (long long)total_tiles - (long long)wave * gridDim.x);
+            const long long left = (long long)total_tiles - (long long)wave * workers;
+            const unsigned int expect = (unsigned int)(left < workers ? left : workers);
             atomicAdd(ctr, 1u);
             unsigned int seen;
             do {
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
       int stage = 0;
       uint32_t phase = 0;
       uint32_t unit = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < total_tiles; tile += workers) {
         mma_pass<0>(p, tmem_base, smem_base, full0, empty0, tfull, tempty, unit++, stage, phase);
         mma_pass<1>(p, tmem_base, smem_base, full0, empty0, tfull, tempty, unit++, stage, phase);
       }
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(THREADS, 1) ozaki_gemm_kernel(const Params p) 
     const int quarter = warp & 3; /* the TMEM lanes a warp may read: 32 * (warp id % 4) */
     const int half = ew >> 2;     /* columns 0..63 or 64..127 of the tile */
     uint32_t unit = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < total_tiles; tile += workers) {
       int tm, tn;
       tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
       const int row = tm * BM + quarter * 32 + lane;

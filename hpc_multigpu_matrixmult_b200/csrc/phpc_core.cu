@@ -404,11 +404,12 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
   PHPC_REQUIRE(lda >= k && ldb >= n && ldc >= n, "leading dimension smaller than the row length");
   gemm_order_begin(ctx, stream);
   int launches = 0;
+  const char *fl = getenv("PHPC_OZ_FLAGS"), *ts = getenv("PHPC_OZ_TSTAMP"); /* diagnostics only (tools/ozaki_knobs.py) */
+  const int flags = (fl && *fl) ? atoi(fl) : 0;
   const int tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
   const long long tiles = (long long)tiles_m * tiles_n;
   PHPC_REQUIRE(tiles < (1ll << 30), "too many output tiles");
   const size_t m_pad = (size_t)tiles_m * BM, n_pad = (size_t)tiles_n * BN;
-  const char *fl = getenv("PHPC_OZ_FLAGS"), *ts = getenv("PHPC_OZ_TSTAMP"); /* diagnostics only (tools/ozaki_knobs.py) */
   /* grid_width x grid_height of the reference's CLI = number of persistent CTAs (<= 1: one per SM), as for the DMMA kernel */
   int grid = (ctas <= 1) ? ctx->sm_count : (ctas < ctx->sm_count ? ctas : ctx->sm_count);
   if ((long long)grid > tiles) grid = (int)tiles;
@@ -459,7 +460,7 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     p.TB = TB;
     p.guard = guard;
     p.wave_sync = wave_sync;
-    p.flags = (fl && *fl) ? atoi(fl) : 0;
+    p.flags = flags;
     p.tstamp = nullptr;
     if (ts && atoi(ts)) {
       p.tstamp = (unsigned long long *)phpc_buf_reserve(&ctx->ozT, (size_t)tiles * 16);

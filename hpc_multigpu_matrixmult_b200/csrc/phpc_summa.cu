@@ -59,8 +59,11 @@ static int env_int(const char *name, int dflt) {
 /* ------------------------------------------------------------------------- */
 /* schedule (pure host arithmetic)                                            */
 /* ------------------------------------------------------------------------- */
-extern "C" int phpc_summa_schedule_mkn(int M, int K, int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps,
-                                       int *m_out, int *n_out) {
+/* kc_first > 0: the very first chunk (of panel 0) is only kc_first wide.  Nothing can overlap the transfer of the first chunk
+ * (every rank waits for it, and up to c - 1 peers pull it from one owner at once), so it is kept small; its short GEMM then
+ * covers the transfer of the first full-size chunk. */
+static int summa_schedule(int M, int K, int N, int r, int c, int pi, int pj, int kc, int kc_first, phpc_summa_step *steps, int max_steps,
+                          int *m_out, int *n_out) {
   if (M <= 0 || K <= 0 || N <= 0 || r <= 0 || c <= 0 || M % r || N % c) return -1;
   const int lcm = r / gcd_int(r, c) * c;
   if (K % lcm) return -1;
@@ -75,8 +78,9 @@ extern "C" int phpc_summa_schedule_mkn(int M, int K, int N, int r, int c, int pi
     const int a_root = k % c, b_root = k % r; /* reference :64-65 */
     const int own_a = (a_root == pj), own_b = (b_root == pi);
     const int b_local_panel = k / r; /* how many panels this row owned before k (own_b) */
-    for (int k_in = 0, q = 0; k_in < pk; k_in += kc, ++q) {
-      const int width = (pk - k_in < kc) ? pk - k_in : kc;
+    for (int k_in = 0, width = 0; k_in < pk; k_in += width) {
+      width = (pk - k_in < kc) ? pk - k_in : kc;
+      if (k == 0 && k_in == 0 && kc_first > 0 && kc_first < width) width = kc_first;
       if (steps && count < max_steps) {
         phpc_summa_step *s = &steps[count];
         s->panel = k;
@@ -94,6 +98,11 @@ extern "C" int phpc_summa_schedule_mkn(int M, int K, int N, int r, int c, int pi
     }
   }
   return count;
+}
+
+extern "C" int phpc_summa_schedule_mkn(int M, int K, int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps,
+                                       int *m_out, int *n_out) {
+  return summa_schedule(M, K, N, r, c, pi, pj, kc, 0, steps, max_steps, m_out, n_out);
 }
 
 extern "C" int phpc_summa_schedule(int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps, int *m_out,
@@ -162,6 +171,7 @@ static void nccl_grid_get(MPI_Comm grid_comm, int size, int rank, int r, int c, 
 struct phpc_summa {
   MPI_Comm grid_comm;
   int rank, size;
+  int kc_first = 0;                       /* width of the very first K chunk on a multi-rank grid (0 = like the others) */
   int N, r, c, pi, pj, lcm, m, n, pk, kc; /* N = global columns of B and C (= leading dimension of host B, C) */
   int gM, gK;                             /* global rows of A and C, global K (= leading dimension of host A); square: all N */
   long long ldn;   /* padded leading dimension of B chunks and of C */
@@ -230,10 +240,12 @@ extern "C" phpc_summa *phpc_summa_create_mkn(MPI_Comm grid_comm, int gm, int gk,
   s->ldn = phpc_pad_ld(s->n);
   s->lda_k = phpc_pad_ld(kc);
 
-  const int nsteps = phpc_summa_schedule_mkn(gm, gk, n, s->r, s->c, s->pi, s->pj, kc, nullptr, 0, nullptr, nullptr);
+  if (s->size > 1 && kc >= 4096) s->kc_first = env_int("PHPC_KC_FIRST", 2048) / 128 * 128;
+  const int kf = s->kc_first;
+  const int nsteps = summa_schedule(gm, gk, n, s->r, s->c, s->pi, s->pj, kc, kf, nullptr, 0, nullptr, nullptr);
   PHPC_REQUIRE(nsteps > 0, "empty SUMMA schedule");
   s->steps.resize(nsteps);
-  phpc_summa_schedule_mkn(gm, gk, n, s->r, s->c, s->pi, s->pj, kc, s->steps.data(), nsteps, nullptr, nullptr);
+  summa_schedule(gm, gk, n, s->r, s->c, s->pi, s->pj, kc, kf, s->steps.data(), nsteps, nullptr, nullptr);
 
   double t0 = now_s();
   phpc_b200_set_device(pick_device(s->rank));
@@ -277,12 +289,12 @@ extern "C" phpc_summa *phpc_summa_create_mkn(MPI_Comm grid_comm, int gm, int gk,
   {
     std::vector<phpc_summa_step> tmp(nsteps);
     for (int pj2 = 0; pj2 < s->c; ++pj2) {
-      phpc_summa_schedule_mkn(gm, gk, n, s->r, s->c, s->pi, pj2, kc, tmp.data(), nsteps, nullptr, nullptr);
+      summa_schedule(gm, gk, n, s->r, s->c, s->pi, pj2, kc, kf, tmp.data(), nsteps, nullptr, nullptr);
       for (int q = 0; q < nsteps; ++q)
         if (tmp[q].own_a) s->root_a_off[q] = tmp[q].a_off;
     }
     for (int pi2 = 0; pi2 < s->r; ++pi2) {
-      phpc_summa_schedule_mkn(gm, gk, n, s->r, s->c, pi2, s->pj, kc, tmp.data(), nsteps, nullptr, nullptr);
+      summa_schedule(gm, gk, n, s->r, s->c, pi2, s->pj, kc, kf, tmp.data(), nsteps, nullptr, nullptr);
       for (int q = 0; q < nsteps; ++q)
         if (tmp[q].own_b) s->root_b_off[q] = tmp[q].b_off;
     }
@@ -441,6 +453,12 @@ extern "C" void phpc_summa_destroy(phpc_summa *s) {
   cudaEventDestroy(s->ev_user);
   delete s;
   PHPC_TRACE(rank_dbg, "destroy", t0);
+}
+
+extern "C" void phpc_summa_chunks(const phpc_summa *s, int *kc, int *kc_first, int *steps) {
+  if (kc) *kc = s->kc;
+  if (kc_first) *kc_first = s->kc_first;
+  if (steps) *steps = (int)s->steps.size();
 }
 
 extern "C" void phpc_summa_global(const phpc_summa *s, int mkn[3]) {
@@ -653,7 +671,16 @@ static void summa_run(phpc_summa *s, int backend, int ctas, void *user_stream, p
       phpc_launch_cublas(ctx, a, lda, b, s->ldn, s->dC, s->ldn, s->m, st.width, s->n, comp);
       ++launches;
     } else if (backend == PHPC_BACKEND_OZAKI) {
-      launches += phpc_launch_ozaki(ctx, a, lda, b, s->ldn, s->dC, s->ldn, s->m, st.width, s->n, ctas, comp);
+      /* NCCL transport: the persistent tcgen05 grid waits for ALL its CTAs to be resident, so a broadcast kernel that cannot
+       * get an SM until the GEMM ends (and whose peers then wait for it) serialises transfer and compute completely
+       * (measured: 73 % exposed on 8 GPUs).  While broadcasts are in flight the GEMM leaves SMs free for them. */
+      int use = ctas;
+      if (any_comm && !pull && q + 1 < nsteps) {
+        const int base = (ctas <= 1 || ctas > ctx->sm_count) ? ctx->sm_count : ctas;
+        const int reserve = env_int("PHPC_COMM_SMS", 8);
+        use = base - reserve > 2 ? base - reserve : 2;
+      }
+      launches += phpc_launch_ozaki(ctx, a, lda, b, s->ldn, s->dC, s->ldn, s->m, st.width, s->n, use, comp);
     } else {
       int use = ctas;
       if (any_comm && !pull && comm_sms > 0 && q + 1 < nsteps) {
@@ -853,9 +880,17 @@ extern "C" void phpc_summa_run_host(phpc_summa *s, int backend, int ctas, const 
     summa_run_host_banded(s, backend, ctas, A, B, C, bands, stats ? stats : &local);
     return;
   }
+  const double t0 = now_s();
   summa_run(s, backend, ctas, nullptr, stats ? stats : &local, A, B, C, true);
+  const double t1 = now_s();
   phpc_summa_download_c(s, C, gather);
+  const double t2 = now_s();
   if (s->size > 1 && s->transport == 1) MPI_Barrier(s->grid_comm); /* peers are done pulling before the next upload */
+  if (getenv("PHPC_DEBUG")) {
+    const phpc_summa_stats *st = stats ? stats : &local;
+    fprintf(stderr, "[phpc %d] run_host: uploads+loop %.1f ms (device: loop %.1f ms, GEMMs %.1f ms), download+gather %.1f ms, final barrier %.1f ms\n",
+            s->rank, (t1 - t0) * 1e3, st->total_ms, st->gemm_ms, (t2 - t1) * 1e3, (now_s() - t2) * 1e3);
+  }
 }
 
 /* ------------------------------------------------------------------------- */

@@ -114,6 +114,9 @@ phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc);
  * panels of width K/lcm as in the square case.  Host matrices passed to upload / run_host / download_c are the FULL
  * A (M x K, ld K), B (K x N, ld N), C (M x N, ld N).  phpc_summa_create(comm, n, kc) == phpc_summa_create_mkn(comm, n, n, n, kc). */
 phpc_summa *phpc_summa_create_mkn(MPI_Comm grid_comm, int m, int k, int n, int kc);
+/* K chunking of the object: chunk width, width of the very first chunk (multi-rank grids start with a short chunk, 2048 by
+ * default / PHPC_KC_FIRST, because nothing can overlap the transfer of the first chunk; 0 = like the others), number of steps. */
+void phpc_summa_chunks(const phpc_summa *s, int *kc, int *kc_first, int *steps);
 /* Global problem size {M, K, N} of the object. */
 void phpc_summa_global(const phpc_summa *s, int mkn[3]);
 void phpc_summa_destroy(phpc_summa *s);
