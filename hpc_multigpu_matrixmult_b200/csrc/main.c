@@ -98,6 +98,10 @@ int main(int argc, char *argv[]) {
 
   MPI_ASSERT(phpc_b200_device_count() > 0);
   const int gpu_count = 1; /* GPUs driven by one rank */
+  { /* bind the rank to its GPU (and to that GPU's NUMA node) BEFORE the host matrices are allocated and first touched */
+    const char *lr = getenv("PHPC_DEVICE") ? getenv("PHPC_DEVICE") : getenv("LOCAL_RANK");
+    phpc_b200_set_device((lr ? atoi(lr) : rank) % phpc_b200_device_count());
+  }
 
   period[0] = period[1] = 1;
   MPI_Comm grid_comm;

@@ -103,9 +103,58 @@ extern "C" int phpc_b200_device_count(void) {
   return n;
 }
 
+/* Host matrices are first touched by the rank that uploads them: run the rank on the CPUs of ITS GPU's NUMA node, so that its
+ * pages and its PCIe link sit on the same socket (8 ranks moving 25.8 + 16 GB per call through one socket's memory controllers
+ * and the inter-socket link is what bounds the host-sourced call on an 8-GPU box).  PHPC_NUMA=0 leaves the affinity alone. */
+#include <sched.h>
+static void bind_to_gpu_numa_node(int device) {
+  const char *e = getenv("PHPC_NUMA");
+  if (e && atoi(e) == 0) return;
+  char bus[32] = {0}, path[128];
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  for (char *c = bus; *c; ++c)
+    if (*c >= 'A' && *c <= 'F') *c += 'a' - 'A';
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE *f = fopen(path, "r");
+  int node = -1;
+  if (f) {
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+  }
+  if (node >= 0) {
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    cpu_set_t want, have, both;
+    CPU_ZERO(&want);
+    if (f) {
+      int a, b;
+      char sep;
+      while (fscanf(f, "%d", &a) == 1) {
+        b = a;
+        if (fscanf(f, "%c", &sep) == 1 && sep == '-') {
+          if (fscanf(f, "%d", &b) != 1) b = a;
+          if (fscanf(f, "%c", &sep) != 1) sep = 0;
+        }
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c) CPU_SET(c, &want);
+      }
+      fclose(f);
+    }
+    if (sched_getaffinity(0, sizeof have, &have) == 0) {
+      CPU_AND(&both, &want, &have);
+      if (CPU_COUNT(&both) > 0) sched_setaffinity(0, sizeof both, &both);
+    }
+  }
+  if (getenv("PHPC_DEBUG")) fprintf(stderr, "[phpc] device %d (%s): NUMA node %d\n", device, bus, node);
+}
+
 extern "C" void phpc_b200_set_device(int device) {
+  const bool first = g_bound_device != device;
   g_bound_device = device;
   phpc_ctx(device);
+  if (first) bind_to_gpu_numa_node(device);
 }
 
 extern "C" int phpc_b200_get_device(void) { return phpc_cur_ctx()->device; }
@@ -166,6 +215,7 @@ extern "C" void phpc_host_free_pinned(void *p) {
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <unistd.h>
 
 #include <string>
@@ -186,7 +236,14 @@ extern "C" void *phpc_host_malloc_shared(size_t bytes) {
   const size_t len = (bytes + 4095) / 4096 * 4096;
   int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
   if (fd < 0) return nullptr;
-  if (posix_fallocate(fd, 0, (off_t)len) != 0) { /* reserve now: a full /dev/shm must not turn into SIGBUS later */
+  /* every GPU of the node writes into this allocation: spread its pages over all NUMA nodes (MPOL_INTERLEAVE while the pages
+   * are allocated) instead of piling them onto the node of the allocating rank */
+  unsigned long all_nodes[16];
+  memset(all_nodes, 0xff, sizeof all_nodes);
+  const bool interleaved = syscall(SYS_set_mempolicy, 3 /* MPOL_INTERLEAVE */, all_nodes, 64ul) == 0;
+  const int rc = posix_fallocate(fd, 0, (off_t)len); /* reserve now: a full /dev/shm must not turn into SIGBUS later */
+  if (interleaved) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0ul);
+  if (rc != 0) {
     close(fd);
     shm_unlink(name);
     return nullptr;
