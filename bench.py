@@ -11,16 +11,20 @@ A "step" is one whole SUMMA  C += A*B  (FP64, N x N, 2*N^3 flop) on the r x c pr
 grid (1x1, 1x2, 2x2, 2x4 for 1, 2, 4, 8 GPUs), one process per GPU.  N is fixed as the
 GPU count grows ("scaling": "strong").
   value  device-resident: every rank's owned A/B blocks already in HBM, timed with CUDA
-         events on the launching stream around K steps, max over ranks.
+         events on the launching stream around K steps, max over ranks; afterwards every rank checks
+         sampled elements of its C block against exactly summed FP64 dot products (`value_verified`).
   e2e    the reference-facing C-ABI call phpc_gemm_summa_cuda() on FULL N x N HOST
          matrices: upload of the owned blocks, the k-loop, download of C and the gather
          to rank 0 are all inside the timed region (wall clock around a synchronous call,
-         bracketed by barriers, max over ranks).
-  roofline  the DMMA GEMM kernel: 2*m*k*n flop per launch / mean launch duration (CUDA
-         events recorded around every launch inside the timed region) against the
-         FP64 peak measured on this pool (profiles/fp64_peak_r01.json).
+         bracketed by barriers, max over ranks); verified on every rank, rank 0 across every block.
+  roofline  the tcgen05 GEMM kernel (phpc::oz::ozaki_gemm_kernel): 2*m*k*n*28 int8 operations per
+         local GEMM / mean local-GEMM duration (CUDA events recorded around every launch inside the
+         timed region) against the int8 tensor peaks measured on this pool with tools/umma_rate.cu
+         (burst: profiles/umma_rate_r01.jsonl; sustained on random operands: profiles/umma_rate_sustained_r02.jsonl);
+         the native-FP64 DMMA kernel and cuBLAS Dgemm are measured in the same run and reported beside it.
   cpu_baseline  the reference's iterative.c (oracle/_ref, compiled unchanged with the
-         reference's flags) on ONE host core at a bounded size.
+         reference's flags) on ONE host core at a bounded size; beside it the reference's own
+         SUMMA on all host cores and the reference's own CUDA+MPI build on the same GPUs.
 torch is plumbing only (process group, events, synchronize); all math goes through
 libphpc_b200.so.  The oracle is touched only by the cpu_baseline / --impl reference legs.
 """
