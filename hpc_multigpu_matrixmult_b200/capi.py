@@ -59,7 +59,7 @@ class HostOp(ctypes.Structure):
     ]
 
 
-HOP_UPLOAD_C, HOP_UPLOAD_A, HOP_UPLOAD_B, HOP_GEMM, HOP_DOWNLOAD_C = range(5)
+HOP_UPLOAD_C, HOP_UPLOAD_A, HOP_UPLOAD_B, HOP_GEMM, HOP_DOWNLOAD_C, HOP_ZERO_C, HOP_ADD_C = range(7)
 
 
 class SummaStats(ctypes.Structure):

@@ -31,6 +31,8 @@
     if (r__ != ncclSuccess) phpc_die(#call, ncclGetErrorString(r__), __FILE__, __LINE__); \
   } while (0)
 
+#define PHPC_MAX_HOST_BANDS 4
+
 static int gcd_int(int a, int b) {
   while (b) {
     int t = a % b;
@@ -197,6 +199,11 @@ struct phpc_summa {
   std::vector<cudaEvent_t> ev_g0, ev_g1;      /* per step: GEMM start / stop */
   std::vector<cudaEvent_t> ev_up;             /* per step: owned chunks uploaded (host-sourced runs); interprocess events on a multi-rank pull grid */
   std::vector<cudaEvent_t> peer_up_a, peer_up_b; /* per step: the A / B root's ev_up of that step, opened through CUDA IPC (null when own) */
+  /* multi-rank pull grids carry PHPC_MAX_HOST_BANDS x nsteps upload events (index band * nsteps + step): the banded
+   * host-sourced run uploads the A rows of one row band at a time */
+  std::vector<cudaEvent_t> ev_c0, ev_band;     /* per band: caller's C band uploaded / band final in HBM */
+  std::vector<cudaEvent_t> ev_bg0, ev_bg1;     /* per (band, step): GEMM start / stop of the banded run */
+  cudaStream_t d2h[2] = {nullptr, nullptr};    /* downloads of finished bands: own C, rank 0's shared C */
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_user = nullptr, ev_cup = nullptr;
 };
 
@@ -382,28 +389,31 @@ extern "C" phpc_summa *phpc_summa_create_mkn(MPI_Comm grid_comm, int gm, int gk,
   }
   s->ev_g0.resize(nsteps);
   s->ev_g1.resize(nsteps);
-  s->ev_up.resize(nsteps);
+  const bool ipc_events = s->size > 1 && s->transport == 1;
+  const int nup = ipc_events ? PHPC_MAX_HOST_BANDS * nsteps : nsteps;
+  s->ev_up.resize(nup);
   for (int q = 0; q < nsteps; ++q) {
     CUDA_CHECK(cudaEventCreate(&s->ev_g0[q]));
     CUDA_CHECK(cudaEventCreate(&s->ev_g1[q]));
-    CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_up[q], cudaEventDisableTiming | ((s->size > 1 && s->transport == 1) ? cudaEventInterprocess : 0)));
   }
-  s->peer_up_a.assign(nsteps, nullptr);
+  for (int q = 0; q < nup; ++q) CUDA_CHECK(cudaEventCreateWithFlags(&s->ev_up[q], cudaEventDisableTiming | (ipc_events ? cudaEventInterprocess : 0)));
+  s->peer_up_a.assign(nup, nullptr);
   s->peer_up_b.assign(nsteps, nullptr);
   if (s->size > 1 && s->transport == 1) {
     /* "owned chunks of step q are in my store" as an event the peers that pull the chunk can wait for on THEIR streams:
      * host-sourced runs upload chunk by chunk under the GEMMs instead of "upload everything, synchronise, barrier" */
-    std::vector<cudaIpcEventHandle_t> mine(nsteps), theirs(nsteps);
-    for (int q = 0; q < nsteps; ++q) CUDA_CHECK(cudaIpcGetEventHandle(&mine[q], s->ev_up[q]));
+    std::vector<cudaIpcEventHandle_t> mine(nup), theirs(nup);
+    for (int q = 0; q < nup; ++q) CUDA_CHECK(cudaIpcGetEventHandle(&mine[q], s->ev_up[q]));
     for (int root = 0; root < s->size; ++root) {
       if (root == s->rank) theirs = mine;
-      MPI_Bcast(theirs.data(), (int)(sizeof(cudaIpcEventHandle_t) * nsteps), MPI_BYTE, root, grid_comm);
+      MPI_Bcast(theirs.data(), (int)(sizeof(cudaIpcEventHandle_t) * nup), MPI_BYTE, root, grid_comm);
       if (root == s->rank) continue;
       const int ri = root / s->c, rj = root % s->c;
-      for (int q = 0; q < nsteps; ++q) {
+      for (int g = 0; g < nup; ++g) {
+        const int q = g % nsteps;
         const phpc_summa_step &st = s->steps[q];
-        if (ri == s->pi && rj == st.a_root && !st.own_a) CUDA_CHECK(cudaIpcOpenEventHandle(&s->peer_up_a[q], theirs[q]));
-        if (rj == s->pj && ri == st.b_root && !st.own_b) CUDA_CHECK(cudaIpcOpenEventHandle(&s->peer_up_b[q], theirs[q]));
+        if (ri == s->pi && rj == st.a_root && !st.own_a) CUDA_CHECK(cudaIpcOpenEventHandle(&s->peer_up_a[g], theirs[g]));
+        if (g < nsteps && rj == s->pj && ri == st.b_root && !st.own_b) CUDA_CHECK(cudaIpcOpenEventHandle(&s->peer_up_b[q], theirs[q]));
       }
     }
   }
@@ -447,6 +457,12 @@ extern "C" void phpc_summa_destroy(phpc_summa *s) {
     if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : s->peer_up_b)
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->ev_c0) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->ev_band) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->ev_bg0) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->ev_bg1) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i)
+    if (s->d2h[i]) cudaStreamDestroy(s->d2h[i]);
   cudaEventDestroy(s->ev_cup);
   cudaEventDestroy(s->ev_begin);
   cudaEventDestroy(s->ev_end);
@@ -799,6 +815,16 @@ static int cb_gemm(void *self, int stream, const double *a, long long lda, const
   return launches;
 }
 
+static void cb_zero(void *self, int stream, double *dst, size_t count) {
+  CudaBandBackend *b = (CudaBandBackend *)self;
+  CUDA_CHECK(cudaMemsetAsync(dst, 0, count * sizeof(double), b->streams[stream]));
+}
+static void cb_add(void *self, int stream, double *dst, const double *src, size_t count) {
+  CudaBandBackend *b = (CudaBandBackend *)self;
+  add_inplace_kernel<<<b->s->ctx->sm_count * 4, 256, 0, b->streams[stream]>>>(dst, src, count);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 static void summa_run_host_banded(phpc_summa *s, int backend, int ctas, const double *hA, const double *hB, double *hC, int bands,
                                   phpc_summa_stats *stats) {
   PHPC_REQUIRE(s->size == 1, "the band pipeline is the single-rank host path");
@@ -816,7 +842,8 @@ static void summa_run_host_banded(phpc_summa *s, int backend, int ctas, const do
   cb.streams[0] = ctx->copy;
   cb.streams[1] = ctx->compute;
   cb.streams[2] = ctx->comm; /* idle on one GPU: it carries the downloads */
-  phpc::BandBackend be = {&cb, cb_copy2d, cb_record, cb_wait, cb_gemm};
+  phpc::BandBackend be = {&cb, cb_copy2d, cb_record, cb_wait, cb_gemm, cb_zero, cb_add};
+  if (!s->dC0) CUDA_CHECK(cudaMalloc(&s->dC0, s->c_elems * sizeof(double)));
   phpc::BandGeom g;
   g.N = s->N;
   g.lda_host = s->gK;
@@ -830,6 +857,7 @@ static void summa_run_host_banded(phpc_summa *s, int backend, int ctas, const do
   g.dA = s->dA;
   g.dB = s->dB;
   g.dC = s->dC;
+  g.dC0 = s->dC0;
 
   CUDA_CHECK(cudaEventRecord(s->ev_begin, ctx->compute));
   CUDA_CHECK(cudaStreamWaitEvent(cb.streams[0], s->ev_begin, 0));
@@ -859,12 +887,180 @@ static void summa_run_host_banded(phpc_summa *s, int backend, int ctas, const do
   for (cudaEvent_t e : cb.g1) CUDA_CHECK(cudaEventDestroy(e));
 }
 
-/* Row bands of the single-GPU host-sourced run: PHPC_HOST_BANDS, else 4 once the block is big enough
- * for the C transfers to matter (>= 8192 rows), else 1 (= the chunk-pipelined loop above).  Why 4 at
- * N = 32768 (PCIe ~55 GB/s, GEMM ~1 s): band 0 must bring all of B (8.6 GB) + its A and C bands
- * (2 x 2.1 GB) = 0.23 s of H2D under 0.26 s of compute, so it is not upload bound (with 8 bands it is);
- * every band repeats the split of the B chunks (Ozaki) = +0.4 % per band; the exposed tail is the last
- * band's download (0.04 s). */
+/* ------------------------------------------------------------------------- */
+/* band-pipelined host-sourced run, several ranks                             */
+/* ------------------------------------------------------------------------- */
+struct ShareInfo { /* where rank 0's result matrix lives when every rank can map it (phpc_host_malloc_shared) */
+  int shared;
+  char name[64];
+  unsigned long long off, bytes;
+};
+
+/*
+ * The host side bounds the multi-rank call (8 GPUs, N = 32768: 3.2 GB up and 2.1 GB down per rank against 80 ms of GEMMs),
+ * and with the K-outer loop the first byte of C can only leave when the last chunk has been multiplied, so uploads and
+ * downloads ran one after the other.  Here the rank's C block is cut into row bands and the SUMMA k-loop runs once per band:
+ * band b needs the A rows of that band only (uploaded and pulled per band; a band of a stored chunk is contiguous) and every
+ * B chunk (uploaded once, pulled again per band: NVLink has the headroom), and it is final, and on its way to the host over
+ * the D2H direction of the link, while the uploads and GEMMs of band b+1 proceed.  Per element the K chunks are still added
+ * in ascending order.  Used when rank 0's C is node-shared memory (every rank then writes its bands straight into it).
+ */
+static void summa_run_host_multi_banded(phpc_summa *s, int backend, int ctas, const double *hA, const double *hB, double *hC, const ShareInfo &sh,
+                                        int bands, phpc_summa_stats *stats) {
+  DeviceCtx *ctx = s->ctx;
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t comm = ctx->comm, comm2 = ctx->comm2, comp = ctx->compute, copy = ctx->copy;
+  const int nsteps = (int)s->steps.size();
+  int rows_per_band = (s->m + bands - 1) / bands;
+  rows_per_band = (rows_per_band + 127) / 128 * 128;
+  const int nb = (s->m + rows_per_band - 1) / rows_per_band;
+  PHPC_REQUIRE(nb <= PHPC_MAX_HOST_BANDS, "too many host row bands");
+  const int total = nb * nsteps;
+  const size_t N = (size_t)s->N, K = (size_t)s->gK;
+  for (int i = 0; i < 2; ++i)
+    if (!s->d2h[i]) CUDA_CHECK(cudaStreamCreateWithFlags(&s->d2h[i], cudaStreamNonBlocking));
+  while ((int)s->ev_c0.size() < nb) {
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    s->ev_c0.push_back(a);
+    s->ev_band.push_back(b);
+  }
+  while ((int)s->ev_bg0.size() < total) {
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a));
+    CUDA_CHECK(cudaEventCreate(&b));
+    s->ev_bg0.push_back(a);
+    s->ev_bg1.push_back(b);
+  }
+  if (hC && !s->dC0) CUDA_CHECK(cudaMalloc(&s->dC0, s->c_elems * sizeof(double)));
+  char *shared_base = nullptr;
+  if (s->rank != 0) {
+    const unsigned long long blk_off = sh.off + ((unsigned long long)s->pi * s->m * N + (unsigned long long)s->pj * s->n) * sizeof(double);
+    const unsigned long long blk_len = ((unsigned long long)(s->m - 1) * N + s->n) * sizeof(double);
+    shared_base = (char *)phpc_host_shared_map(sh.name, sh.bytes, blk_off, blk_len) + blk_off;
+  }
+
+  CUDA_CHECK(cudaEventRecord(s->ev_begin, comp));
+  for (cudaStream_t st : {comm, comm2, copy, s->d2h[0], s->d2h[1]}) CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_begin, 0));
+  CUDA_CHECK(cudaMemsetAsync(s->dC, 0, s->c_elems * sizeof(double), comp));
+
+  /* 1. every upload of the call, band after band, each followed by an interprocess event */
+  for (int b = 0; b < nb; ++b) {
+    const int row0 = b * rows_per_band, rows = (s->m - row0 < rows_per_band) ? s->m - row0 : rows_per_band;
+    for (int q = 0; q < nsteps; ++q) {
+      const phpc_summa_step &st = s->steps[q];
+      if (st.own_a) {
+        const size_t ld = phpc_pad_ld(st.width);
+        CUDA_CHECK(cudaMemcpy2DAsync(s->dA + st.a_off + (size_t)row0 * ld, ld * sizeof(double), hA + ((size_t)s->pi * s->m + row0) * K + (size_t)st.k0,
+                                     K * sizeof(double), (size_t)st.width * sizeof(double), rows, cudaMemcpyHostToDevice, copy));
+      }
+      if (b == 0 && st.own_b)
+        CUDA_CHECK(cudaMemcpy2DAsync(s->dB + st.b_off, s->ldn * sizeof(double), hB + (size_t)st.k0 * N + (size_t)s->pj * s->n, N * sizeof(double),
+                                     (size_t)s->n * sizeof(double), st.width, cudaMemcpyHostToDevice, copy));
+      CUDA_CHECK(cudaEventRecord(s->ev_up[b * nsteps + q], copy));
+    }
+    if (hC) {
+      CUDA_CHECK(cudaMemcpy2DAsync(s->dC0 + (size_t)row0 * s->ldn, s->ldn * sizeof(double), hC + ((size_t)s->pi * s->m + row0) * N + (size_t)s->pj * s->n,
+                                   N * sizeof(double), (size_t)s->n * sizeof(double), rows, cudaMemcpyHostToDevice, copy));
+      if (s->ldn != s->n)
+        CUDA_CHECK(cudaMemset2DAsync(s->dC0 + (size_t)row0 * s->ldn + s->n, s->ldn * sizeof(double), 0, (size_t)(s->ldn - s->n) * sizeof(double), rows, copy));
+    }
+    CUDA_CHECK(cudaEventRecord(s->ev_c0[b], copy));
+  }
+  MPI_Barrier(s->grid_comm); /* orders the ENQUEUE of the records above before the peers enqueue their waits */
+
+  /* 2. the k-loop, once per band */
+  int launches = 0, broadcasts = 0;
+  long long bytes_rx = 0;
+  auto stage_in = [&](int g) {
+    const int b = g / nsteps, q = g % nsteps, slot = g % s->nbuf;
+    const phpc_summa_step &st = s->steps[q];
+    const int row0 = b * rows_per_band, rows = (s->m - row0 < rows_per_band) ? s->m - row0 : rows_per_band;
+    if (s->c > 1 && !st.own_a) {
+      const size_t ld = phpc_pad_ld(st.width), count = (size_t)rows * ld;
+      if (g >= s->nbuf) CUDA_CHECK(cudaStreamWaitEvent(comm, s->ev_free[slot], 0));
+      CUDA_CHECK(cudaStreamWaitEvent(comm, s->peer_up_a[b * nsteps + q], 0));
+      CUDA_CHECK(cudaMemcpyAsync(s->ringA + (size_t)slot * s->ringA_elems, s->peerA[st.a_root] + s->root_a_off[q] + (size_t)row0 * ld, count * 8,
+                                 cudaMemcpyDeviceToDevice, comm));
+      ++broadcasts;
+      bytes_rx += (long long)count * 8;
+    }
+    CUDA_CHECK(cudaEventRecord(s->ev_bcast[slot], comm));
+    if (s->r > 1 && !st.own_b) {
+      const size_t count = (size_t)st.width * s->ldn;
+      if (g >= s->nbuf) CUDA_CHECK(cudaStreamWaitEvent(comm2, s->ev_free[slot], 0));
+      CUDA_CHECK(cudaStreamWaitEvent(comm2, s->peer_up_b[q], 0));
+      CUDA_CHECK(cudaMemcpyAsync(s->ringB + (size_t)slot * s->ringB_elems, s->peerB[st.b_root] + s->root_b_off[q], count * 8, cudaMemcpyDeviceToDevice,
+                                 comm2));
+      ++broadcasts;
+      bytes_rx += (long long)count * 8;
+    }
+    CUDA_CHECK(cudaEventRecord(s->ev_bcast2[slot], comm2));
+  };
+  int issued = 0;
+  stage_in(issued++);
+  for (int g = 0; g < total; ++g) {
+    const int b = g / nsteps, q = g % nsteps, slot = g % s->nbuf;
+    const phpc_summa_step &st = s->steps[q];
+    const int row0 = b * rows_per_band, rows = (s->m - row0 < rows_per_band) ? s->m - row0 : rows_per_band;
+    CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_bcast[slot], 0));
+    CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_bcast2[slot], 0));
+    if (st.own_a) CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_up[b * nsteps + q], 0));
+    if (st.own_b) CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_up[q], 0));
+    const long long lda = phpc_pad_ld(st.width);
+    const double *a = st.own_a ? s->dA + st.a_off + (size_t)row0 * lda : s->ringA + (size_t)slot * s->ringA_elems;
+    const double *bm = st.own_b ? s->dB + st.b_off : s->ringB + (size_t)slot * s->ringB_elems;
+    CUDA_CHECK(cudaEventRecord(s->ev_bg0[g], comp));
+    launches += launch_local_gemm(s, backend, ctas, a, lda, bm, s->dC + (size_t)row0 * s->ldn, rows, st.width, comp);
+    CUDA_CHECK(cudaEventRecord(s->ev_bg1[g], comp));
+    CUDA_CHECK(cudaEventRecord(s->ev_free[slot], comp));
+    while (issued < total && issued < g + s->nbuf) stage_in(issued++);
+    if (q == nsteps - 1) { /* the band is complete: add the caller's C band, send it home */
+      if (hC) {
+        CUDA_CHECK(cudaStreamWaitEvent(comp, s->ev_c0[b], 0));
+        add_inplace_kernel<<<ctx->sm_count * 4, 256, 0, comp>>>(s->dC + (size_t)row0 * s->ldn, s->dC0 + (size_t)row0 * s->ldn, (size_t)rows * s->ldn);
+        CUDA_CHECK(cudaGetLastError());
+      }
+      CUDA_CHECK(cudaEventRecord(s->ev_band[b], comp));
+      const size_t row_bytes = (size_t)s->n * sizeof(double);
+      if (s->rank != 0) { /* first into rank 0's result: that is the copy everybody waits for */
+        CUDA_CHECK(cudaStreamWaitEvent(s->d2h[1], s->ev_band[b], 0));
+        CUDA_CHECK(cudaMemcpy2DAsync(shared_base + (size_t)row0 * N * sizeof(double), N * sizeof(double), s->dC + (size_t)row0 * s->ldn,
+                                     s->ldn * sizeof(double), row_bytes, rows, cudaMemcpyDeviceToHost, s->d2h[1]));
+      }
+      CUDA_CHECK(cudaStreamWaitEvent(s->d2h[0], s->ev_band[b], 0));
+      CUDA_CHECK(cudaMemcpy2DAsync(hC + ((size_t)s->pi * s->m + row0) * N + (size_t)s->pj * s->n, N * sizeof(double), s->dC + (size_t)row0 * s->ldn,
+                                   s->ldn * sizeof(double), row_bytes, rows, cudaMemcpyDeviceToHost, s->d2h[0]));
+    }
+  }
+  CUDA_CHECK(cudaEventRecord(s->ev_end, comp));
+  for (cudaStream_t st : {comp, comm, comm2, copy, s->d2h[0], s->d2h[1]}) CUDA_CHECK(cudaStreamSynchronize(st));
+  MPI_Barrier(s->grid_comm); /* every band has landed in rank 0's C; nobody is still pulling from a store */
+  if (stats) {
+    float tot = 0.f, gemm = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&tot, s->ev_begin, s->ev_end));
+    for (int g = 0; g < total; ++g) {
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, s->ev_bg0[g], s->ev_bg1[g]));
+      gemm += ms;
+    }
+    stats->total_ms = tot;
+    stats->gemm_ms = gemm;
+    stats->exposed_ms = tot - gemm;
+    stats->steps = total;
+    stats->launches = launches;
+    stats->broadcasts = broadcasts;
+    stats->bytes_received = bytes_rx;
+  }
+}
+
+/* Row bands of the single-GPU host-sourced run: PHPC_HOST_BANDS, else 4 once the block is big enough for the C transfers to
+ * matter (>= 8192 rows), else 1.  Bands are 1/2, 1/4, 1/8, 1/8 of the block (host_band_exec.h).  Why, at N = 32768 (PCIe
+ * ~55 GB/s, 8 K chunks of 4096, GEMM 0.64 s): per chunk the first band uploads its A rows + one B chunk (0.54 + 1.07 GB =
+ * 29 ms) under 40 ms of GEMM, and the slack it gains over the 8 chunks pays for the upload of its own C rows (4.3 GB) before
+ * they are added; equal quarters were upload bound in the first band (and waited for the C rows up front: 86 TFLOP/s).  The
+ * exposed tail is the last band's download (1.07 GB, 20 ms).  Every band repeats the split of the B chunks (+0.4 % each). */
 static int host_bands(const phpc_summa *s) {
   if (s->size != 1) return 1;
   const int e = env_int("PHPC_HOST_BANDS", 0);
@@ -876,11 +1072,30 @@ extern "C" void phpc_summa_run_host(phpc_summa *s, int backend, int ctas, const 
                                     phpc_summa_stats *stats) {
   phpc_summa_stats local;
   const int bands = host_bands(s);
-  if (bands > 1 && A && B && C) {
+  if (s->size == 1 && A && B && C) { /* any band count, 1 included: the same arithmetic per element (zeroed block, chunks, + caller's C) */
     summa_run_host_banded(s, backend, ctas, A, B, C, bands, stats ? stats : &local);
     return;
   }
   const double t0 = now_s();
+  if (s->size > 1 && s->transport == 1 && gather && A && B && C) {
+    /* rank 0's C in node-shared memory: the band-pipelined run, every rank delivers its bands itself */
+    ShareInfo sh;
+    memset(&sh, 0, sizeof sh);
+    if (s->rank == 0) sh.shared = phpc_host_shared_lookup(C, sh.name, &sh.off, &sh.bytes);
+    MPI_Bcast(&sh, (int)sizeof sh, MPI_BYTE, 0, s->grid_comm);
+    int mb = env_int("PHPC_HOST_BANDS", 0);
+    if (mb <= 0) mb = s->m >= 4096 ? 4 : (s->m >= 512 ? 2 : 1);
+    if (mb > PHPC_MAX_HOST_BANDS) mb = PHPC_MAX_HOST_BANDS;
+    if (sh.shared) {
+      summa_run_host_multi_banded(s, backend, ctas, A, B, C, sh, mb, stats ? stats : &local);
+      if (getenv("PHPC_DEBUG")) {
+        const phpc_summa_stats *st = stats ? stats : &local;
+        fprintf(stderr, "[phpc %d] run_host (banded, %d bands): %.1f ms wall (device: loop %.1f ms, GEMMs %.1f ms)\n", s->rank, mb, (now_s() - t0) * 1e3,
+                st->total_ms, st->gemm_ms);
+      }
+      return;
+    }
+  }
   summa_run(s, backend, ctas, nullptr, stats ? stats : &local, A, B, C, true);
   const double t1 = now_s();
   phpc_summa_download_c(s, C, gather);

@@ -64,14 +64,17 @@ int phpc_summa_schedule_mkn(int M, int K, int N, int r, int c, int pi, int pj, i
                             int *n_out);
 
 /* One operation of the band-pipelined host-sourced run on a 1 x 1 grid (phpc_summa_run_host): the rank's
- * C block is cut into row bands; band b is uploaded, multiplied over every K chunk and downloaded while
+ * C block is cut into row bands (1/2, 1/4, ... of the block); band b is multiplied over every K chunk into a zeroed
+ * block, the caller's C rows (uploaded in the meantime into a side buffer) are added, and the band is downloaded while
  * band b+1 computes, so the C traffic the reference pays around every kernel (src/phpc_gemm.cu:113,121)
  * hides under the GEMMs together with the A/B uploads. */
-#define PHPC_HOP_UPLOAD_C 0   /* host C band   -> dC band           (copy-in stream)  */
+#define PHPC_HOP_UPLOAD_C 0   /* host C band   -> side buffer band  (copy-in stream)  */
 #define PHPC_HOP_UPLOAD_A 1   /* host A window -> A store (band, step)                */
 #define PHPC_HOP_UPLOAD_B 2   /* host B window -> B store (step)                      */
 #define PHPC_HOP_GEMM 3       /* dC band += A(band, step) * B(step) (compute stream)  */
 #define PHPC_HOP_DOWNLOAD_C 4 /* dC band -> host C band             (copy-out stream) */
+#define PHPC_HOP_ZERO_C 5     /* dC band = 0                        (compute stream)  */
+#define PHPC_HOP_ADD_C 6      /* dC band += side buffer band        (compute stream)  */
 typedef struct phpc_host_op {
   int kind;   /* PHPC_HOP_* */
   int stream; /* 0 = copy-in, 1 = compute, 2 = copy-out; operations of one stream run in list order */
@@ -82,8 +85,8 @@ typedef struct phpc_host_op {
   int deps[3]; /* earlier operations on OTHER streams that must have completed */
 } phpc_host_op;
 
-/* Pure host arithmetic: the operation list for a block of m rows, nsteps K chunks and `bands` row bands
- * whose height is rounded up to a multiple of `align` rows.  Writes up to max_ops entries in issue order
+/* Pure host arithmetic: the operation list for a block of m rows, nsteps K chunks and at most `bands` row bands
+ * (half of what is left each, the last one takes the rest) whose height is rounded up to a multiple of `align` rows.  Writes up to max_ops entries in issue order
  * (dependencies always point backwards) and returns the number of operations. */
 int phpc_host_plan(int m, int nsteps, int bands, int align, phpc_host_op *ops, int max_ops);
 

@@ -62,6 +62,18 @@ def main():
     assert secs > 0
     Cb = np.zeros((N, N))
     capi.phpc_gemm_summa_cublas(comm, A, B, Cb)
+    # the same entry point with rank 0's C in node-shared pinned memory: the band-pipelined multi-rank run, every rank
+    # delivers its bands into rank 0's matrix itself (on one rank this is the ordinary path)
+    shared = capi.host_array_shared(N, N) if rank == 0 else None
+    Cs = shared[0] if shared else np.zeros((N, N))
+    Cs[:] = 0.0
+    capi.phpc_gemm_summa_cuda(comm, A, B, Cs)
+    Cs_copy = Cs.copy()
+    capi.phpc_gemm_summa_cuda(comm, A, B, Cs)  # second pass on the same C: C += A*B with a NONZERO caller block (added at the end of each band)
+    Cs2 = Cs.copy()
+    del Cs
+    if shared:
+        L.phpc_host_free_shared(shared[1])
     # device-resident loop with its own chunking and on-device generation of the blocks
     s = capi.Summa(comm, N, kc)
     s.fill(fill)
@@ -76,7 +88,7 @@ def main():
     s.download_c(Co, gather=True)
     s.destroy()
     if rank == 0:
-        np.save(out, np.stack([C, Cb, Cd, Co]))
+        np.save(out, np.stack([C, Cb, Cd, Co, Cs_copy, Cs2 / 2.0]))
         print(f"steps={st.steps} launches={st.launches} bcasts={st.broadcasts} rx={st.bytes_received} "
               f"total_ms={st.total_ms:.3f} gemm_ms={st.gemm_ms:.3f} exposed_ms={st.exposed_ms:.3f}")
     L.phpc_summa_release_cache()

@@ -59,6 +59,20 @@ int sim_gemm(void *self, int stream, const double *a, long long lda, const doubl
   ++s->gemms;
   return 1;
 }
+void sim_zero(void *self, int stream, double *dst, size_t count) {
+  Sim *s = (Sim *)self;
+  s->queue[stream].push_back({[=]() {
+                                for (size_t i = 0; i < count; ++i) dst[i] = 0.0;
+                              },
+                              nullptr});
+}
+void sim_add(void *self, int stream, double *dst, const double *src, size_t count) {
+  Sim *s = (Sim *)self;
+  s->queue[stream].push_back({[=]() {
+                                for (size_t i = 0; i < count; ++i) dst[i] += src[i];
+                              },
+                              nullptr});
+}
 }  // namespace
 
 /* C += A * B for FULL N x N host matrices through the band pipeline; order 0 = every stream runs eagerly in issue order,
@@ -79,12 +93,12 @@ extern "C" int band_exec_sim(int N, int kc, int bands, int align, const double *
     a_off += (long long)m * phpc::band_pad_ld(st.width);
     steps.push_back(st);
   }
-  std::vector<double> dA((size_t)a_off, NAN), dB((size_t)N * ldn, NAN), dC((size_t)m * ldn, NAN);
+  std::vector<double> dA((size_t)a_off, NAN), dB((size_t)N * ldn, NAN), dC((size_t)m * ldn, NAN), dC0((size_t)m * ldn, NAN);
   const int nops = phpc::host_plan(m, (int)steps.size(), bands, align, nullptr, 0);
   std::vector<phpc_host_op> ops(nops);
   phpc::host_plan(m, (int)steps.size(), bands, align, ops.data(), nops);
   Sim sim;
-  phpc::BandBackend be = {&sim, sim_copy2d, sim_record, sim_wait, sim_gemm};
+  phpc::BandBackend be = {&sim, sim_copy2d, sim_record, sim_wait, sim_gemm, sim_zero, sim_add};
   phpc::BandGeom g;
   g.N = N;
   g.m = m;
@@ -96,6 +110,7 @@ extern "C" int band_exec_sim(int N, int kc, int bands, int align, const double *
   g.dA = dA.data();
   g.dB = dB.data();
   g.dC = dC.data();
+  g.dC0 = dC0.data();
   if (phpc::band_execute(g, ops.data(), nops, hA, hB, hC, be) < 0) return -2;
   std::mt19937 rng(seed);
   for (;;) {

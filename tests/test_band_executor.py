@@ -33,8 +33,11 @@ def test_executor_computes_c_plus_ab_under_any_interleaving(sim, N, kc, bands, a
     C0 = rng.integers(-9, 10, (N, N)).astype(np.float64)
     want = C0 + A @ B
     nsteps = -(-N // kc)
-    rows_per_band = -(-(-(-N // bands)) // align) * align
-    nbands = -(-N // rows_per_band)
+    nbands, left = 0, N  # bands of 1/2, 1/4, ... of what is left, rounded up to `align`; the last one takes the rest
+    while left > 0:
+        nbands += 1
+        rows = left if nbands == bands else min(left, -(-(-(-left // 2)) // align) * align)
+        left -= rows
     for order, seed in [(0, 0)] + [(1, s) for s in range(12)]:
         C = C0.copy()
         gemms = sim.band_exec_sim(N, kc, bands, align, A.ctypes.data_as(dp), B.ctypes.data_as(dp), C.ctypes.data_as(dp), seed, order)

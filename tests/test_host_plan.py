@@ -1,5 +1,6 @@
 """The band pipeline of the single-GPU host-sourced run (phpc_host_plan, include/phpc_summa.h) checked
-on the CPU: the operation list the CUDA executor walks (csrc/phpc_summa.cu, summa_run_host_banded) is
+on the CPU (bands of 1/2, 1/4, ... of the block; each band runs on a zeroed block and the caller's C rows, uploaded
+meanwhile into a side buffer, are added at its end): the operation list the CUDA executor walks (csrc/phpc_summa.cu, summa_run_host_banded) is
 pure host arithmetic, so its ordering is proven here without a GPU:
   * every pair of operations that touch the same memory (one of them writing) is ordered by the
     stream order + the listed dependencies (no read-after-write / write-after-read race);
@@ -16,7 +17,11 @@ def _regions(op, capi):
     """(reads, writes): sets of (buffer, band-or-step) names an operation touches."""
     k = op.kind
     if k == capi.HOP_UPLOAD_C:
-        return {("hC", op.band)}, {("dC", op.band)}
+        return {("hC", op.band)}, {("dC0", op.band)}
+    if k == capi.HOP_ZERO_C:
+        return set(), {("dC", op.band)}
+    if k == capi.HOP_ADD_C:
+        return {("dC0", op.band), ("dC", op.band)}, {("dC", op.band)}
     if k == capi.HOP_UPLOAD_A:
         return {("hA", op.band, op.step)}, {("dA", op.band, op.step)}
     if k == capi.HOP_UPLOAD_B:
@@ -71,10 +76,20 @@ def test_conflicting_operations_are_ordered(capi, m, nsteps, bands, align):
     assert rows[0][0] == 0 and sum(r for _, r in rows) == m
     for (r0, n0), (r1, _) in zip(rows, rows[1:]):
         assert r0 + n0 == r1 and n0 % align == 0
+    sizes = [n0 for _, n0 in rows]
+    assert len(sizes) <= bands and sizes == sorted(sizes, reverse=True)  # 1/2, 1/4, ...: the first band is the tallest
+    if len(sizes) >= 3 and m >= 8 * align * bands:
+        assert sizes[0] >= m // 2 and sizes[1] <= sizes[0] // 2 + align
     kinds = [op.kind for op in ops]
     nb = len(rows)
     assert kinds.count(capi.HOP_GEMM) == nb * nsteps and kinds.count(capi.HOP_UPLOAD_B) == nsteps
     assert kinds.count(capi.HOP_UPLOAD_A) == nb * nsteps and kinds.count(capi.HOP_DOWNLOAD_C) == nb
+    assert kinds.count(capi.HOP_ZERO_C) == nb and kinds.count(capi.HOP_ADD_C) == nb
+    # the caller's C rows are not needed before the first GEMM: within a band they are uploaded after every A window
+    for b in range(nb):
+        idx = {k: [i for i, op in enumerate(ops) if op.kind == k and op.band == b] for k in set(kinds)}
+        assert idx[capi.HOP_UPLOAD_C][0] > max(idx[capi.HOP_UPLOAD_A])
+        assert idx[capi.HOP_ZERO_C][0] < min(idx[capi.HOP_GEMM]) and idx[capi.HOP_ADD_C][0] > max(idx[capi.HOP_GEMM])
 
 
 @pytest.mark.parametrize("m,n,widths,bands,align", [(23, 9, (4, 4, 3), 3, 1), (64, 10, (8, 8), 4, 8), (5, 5, (5,), 2, 1)])
@@ -92,6 +107,7 @@ def test_every_legal_order_gives_c_plus_ab(capi, m, n, widths, bands, align):
         dA = np.full((m, K), np.nan)
         dB = np.full((K, n), np.nan)
         dC = np.full((m, n), np.nan)
+        dC0 = np.full((m, n), np.nan)
         chunk_order = {}
         done, pending = set(), list(range(len(ops)))
         r = random.Random(trial)
@@ -101,7 +117,11 @@ def test_every_legal_order_gives_c_plus_ab(capi, m, n, widths, bands, align):
             op = ops[i]
             rows = slice(op.row0, op.row0 + op.rows)
             if op.kind == capi.HOP_UPLOAD_C:
-                dC[rows] = hC[rows]
+                dC0[rows] = hC[rows]
+            elif op.kind == capi.HOP_ZERO_C:
+                dC[rows] = 0.0
+            elif op.kind == capi.HOP_ADD_C:
+                dC[rows] += dC0[rows]
             elif op.kind == capi.HOP_UPLOAD_A:
                 dA[rows, k0[op.step]:k0[op.step + 1]] = A[rows, k0[op.step]:k0[op.step + 1]]
             elif op.kind == capi.HOP_UPLOAD_B:

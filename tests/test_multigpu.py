@@ -40,8 +40,12 @@ def test_summa_matches_reference_summa_seeded(gpu, oracle, tmp_path, grid, ngpu)
     A = oracle.fill(N, N, kind=1, seed=oracle.SEED_A)
     B = oracle.fill(N, N, kind=1, seed=oracle.SEED_B)
     want = oracle.summa(A, B, *grid)
-    for name, C in zip(("host-entry tcgen05 (default)", "host-entry cublas", "device-resident dmma", "device-resident tcgen05"), Cs):
+    names = ("host-entry tcgen05 (default)", "host-entry cublas", "device-resident dmma", "device-resident tcgen05",
+             "host-entry, rank 0's C node-shared (band-pipelined run, parallel gather)", "the same, second C += pass, halved")
+    assert len(Cs) == len(names)
+    for name, C in zip(names, Cs):
         assert oracle.rel_frobenius(C, want) <= 1e-14, name
+    assert np.array_equal(Cs[4], Cs[0])  # bands only regroup rows: same arithmetic per element as the chunk loop
     assert "bcasts=" in log
 
 
@@ -71,6 +75,24 @@ def test_rectangular_summa_object_api(gpu, oracle, tmp_path, grid, ngpu):
     B2 = oracle.fill(K, N, N=N, kind=1, seed=92)
     C0 = oracle.fill(M, N, N=N, kind=1, seed=93)
     assert oracle.rel_frobenius(Cs[1], oracle.gemm_block(A2, B2, C0)) <= 1e-14
+
+
+@pytest.mark.parametrize("bands", [1, 3, 4])
+def test_band_pipelined_multi_rank_host_run(gpu, oracle, tmp_path, bands):
+    """The multi-rank host-sourced call with rank 0's C in node-shared memory (phpc_host_malloc_shared): the C block travels in
+    row bands, the k-loop runs once per band, every rank writes its finished bands into rank 0's matrix.  Any band count gives
+    the reference's result exactly on its own input (N = 1024) and the chunk loop's result bit for bit."""
+    _need(gpu, 2)
+    grid = (2, 2) if gpu.phpc_b200_device_count() >= 4 else (1, 2)
+    Cs, _ = _run(grid, 1024, 0, tmp_path, kc=96, env={"PHPC_HOST_BANDS": str(bands)})
+    exact = oracle.index_fill_exact(1024)
+    for C in Cs:
+        assert np.array_equal(C, exact)
+    Cr, _ = _run(grid, 640, 1, tmp_path, kc=100, env={"PHPC_HOST_BANDS": str(bands)})
+    assert np.array_equal(Cr[4], Cr[0])
+    A = oracle.fill(640, 640, kind=1, seed=oracle.SEED_A)
+    B = oracle.fill(640, 640, kind=1, seed=oracle.SEED_B)
+    assert oracle.rel_frobenius(Cr[5], oracle.summa(A, B, *grid)) <= 1e-14
 
 
 def test_golden_reference_summa_fixture(gpu, oracle, tmp_path):
