@@ -713,6 +713,25 @@ def product_arm(args):
             else:
                 os.environ["PHPC_PANEL"] = saved
 
+    # ---------------- alternative schedule: stationary C, all panel transfers issued up front ----------------
+    prefetch_all = None
+    if world > 1 and not args.no_secondary:
+        saved = os.environ.get("PHPC_SCHEDULE")
+        os.environ["PHPC_SCHEDULE"] = "prefetch-all"
+        try:
+            s3 = capi.Summa(comm, N, args.kc)
+            s3.fill(capi.FILL_SEEDED)
+            pa = measure(primary, 1, max(1, min(2, args.steps)), False, s=s3)
+            prefetch_all = {"value": pa["tflops"], "unit": UNIT, "ms_per_step": pa["ms"], "exposed_frac": pa["exposed"],
+                            "what": "PHPC_SCHEDULE=prefetch-all: the receive ring holds every K chunk, all copy-engine pulls are issued at the start "
+                                    "(all-gather of the panels), GEMMs consume chunks as they land; default = 3-slot ring"}
+            s3.destroy()
+        finally:
+            if saved is None:
+                os.environ.pop("PHPC_SCHEDULE", None)
+            else:
+                os.environ["PHPC_SCHEDULE"] = saved
+
     # ---------------- e2e through the reference-facing C-ABI on host matrices ----------------
     e2e = None
     if not args.no_e2e:
@@ -780,6 +799,7 @@ def product_arm(args):
             names[secondary]: other,
             "cublas_dgemm": cublas,
             "nccl_broadcast_transport": nccl,
+            "schedule_prefetch_all": prefetch_all,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -152,6 +152,8 @@ def load():
     L.phpc_summa_schedule_mkn.argtypes = [ctypes.c_int] * 8 + [ctypes.POINTER(SummaStep), ctypes.c_int, c_int_p, c_int_p]
     L.phpc_summa_schedule_mkn.restype = ctypes.c_int
     L.phpc_summa_global.argtypes = [ctypes.c_void_p, c_int_p]
+    L.phpc_summa_schedule_first.argtypes = [ctypes.c_int] * 9 + [ctypes.POINTER(SummaStep), ctypes.c_int, c_int_p, c_int_p]
+    L.phpc_summa_schedule_first.restype = ctypes.c_int
     L.phpc_summa_chunks.argtypes = [ctypes.c_void_p, c_int_p, c_int_p, c_int_p]
     L.phpc_summa_destroy.argtypes = [ctypes.c_void_p]
     L.phpc_summa_upload.argtypes = [ctypes.c_void_p, c_double_p, c_double_p, c_double_p]
@@ -285,6 +287,16 @@ def summa_schedule_mkn(M, K, N, r, c, pi, pj, kc=0):
     m, n = ctypes.c_int(), ctypes.c_int()
     L.phpc_summa_schedule_mkn(M, K, N, r, c, pi, pj, kc, steps, count, ctypes.byref(m), ctypes.byref(n))
     return list(steps), m.value, n.value
+
+
+def summa_schedule_first(M, K, N, r, c, pi, pj, kc, kc_first):
+    L = load()
+    count = L.phpc_summa_schedule_first(M, K, N, r, c, pi, pj, kc, kc_first, None, 0, None, None)
+    if count < 0:
+        raise ValueError("M, N must be divisible by the grid dimensions and K by their least common multiple")
+    steps = (SummaStep * count)()
+    L.phpc_summa_schedule_first(M, K, N, r, c, pi, pj, kc, kc_first, steps, count, None, None)
+    return list(steps)
 
 
 def ozaki_config():

@@ -67,6 +67,7 @@ static int env_int(const char *name, int dflt) {
 static int summa_schedule(int M, int K, int N, int r, int c, int pi, int pj, int kc, int kc_first, phpc_summa_step *steps, int max_steps,
                           int *m_out, int *n_out) {
   if (M <= 0 || K <= 0 || N <= 0 || r <= 0 || c <= 0 || M % r || N % c) return -1;
+  if (M <= 0 || K <= 0 || N <= 0 || r <= 0 || c <= 0 || M % r || N % c) return -1;
   const int lcm = r / gcd_int(r, c) * c;
   if (K % lcm) return -1;
   const int m = M / r, n = N / c, pk = K / lcm; /* reference :36-39 (square there: M = K = N) */
@@ -105,6 +106,11 @@ static int summa_schedule(int M, int K, int N, int r, int c, int pi, int pj, int
 extern "C" int phpc_summa_schedule_mkn(int M, int K, int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps,
                                        int *m_out, int *n_out) {
   return summa_schedule(M, K, N, r, c, pi, pj, kc, 0, steps, max_steps, m_out, n_out);
+}
+
+extern "C" int phpc_summa_schedule_first(int M, int K, int N, int r, int c, int pi, int pj, int kc, int kc_first, phpc_summa_step *steps,
+                                         int max_steps, int *m_out, int *n_out) {
+  return summa_schedule(M, K, N, r, c, pi, pj, kc, kc_first, steps, max_steps, m_out, n_out);
 }
 
 extern "C" int phpc_summa_schedule(int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps, int *m_out,
@@ -371,6 +377,15 @@ extern "C" phpc_summa *phpc_summa_create_mkn(MPI_Comm grid_comm, int gm, int gk,
   PHPC_TRACE(s->rank, "create: blocks + ipc", t0);
   s->nbuf = env_int("PHPC_NBUF", 3);
   if (s->nbuf < 2) s->nbuf = 2;
+  {
+    /* Alternative schedule, PHPC_SCHEDULE=prefetch-all: stationary C with an all-gather prefetch.  The ring holds
+     * EVERY chunk of the run, so all panel transfers are issued up front (an all-gather of the A panels along the process row
+     * and of the B panels along the process column, expressed as copy-engine pulls) and the GEMMs consume the chunks as they
+     * land; no slot is ever reused, so no transfer ever waits for a GEMM.  Costs (K/c + K/r) x block bytes of HBM instead of 3
+     * chunks.  Default: the 3-slot ring (transfer of chunk q+1, q+2 under GEMM q). */
+    const char *sch = getenv("PHPC_SCHEDULE");
+    if (sch && !strcmp(sch, "prefetch-all") && s->nbuf < nsteps) s->nbuf = nsteps;
+  }
   if (s->c > 1) {
     s->ringA_elems = (size_t)s->m * s->lda_k;
     CUDA_CHECK(cudaMalloc(&s->ringA, s->ringA_elems * s->nbuf * sizeof(double)));

@@ -63,6 +63,11 @@ int phpc_summa_schedule(int N, int r, int c, int pi, int pj, int kc, phpc_summa_
 int phpc_summa_schedule_mkn(int M, int K, int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps, int *m_out,
                             int *n_out);
 
+/* The schedule multi-rank objects actually run: as above, but the very first chunk (of panel 0) is only kc_first wide
+ * (0 = like the others).  Nothing can overlap the transfer of the first chunk, so it is kept short (phpc_summa_chunks). */
+int phpc_summa_schedule_first(int M, int K, int N, int r, int c, int pi, int pj, int kc, int kc_first, phpc_summa_step *steps, int max_steps,
+                              int *m_out, int *n_out);
+
 /* One operation of the band-pipelined host-sourced run on a 1 x 1 grid (phpc_summa_run_host): the rank's
  * C block is cut into row bands (1/2, 1/4, ... of the block); band b is multiplied over every K chunk into a zeroed
  * block, the caller's C rows (uploaded in the meantime into a side buffer) are added, and the band is downloaded while

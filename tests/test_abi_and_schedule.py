@@ -164,3 +164,22 @@ def test_rectangular_schedule_tiles_k_exactly_and_owners_follow_the_reference(ca
     assert (m, n) == (m2, n2) and [(a.k0, a.width, a.a_off, a.b_off) for a in sq] == [(b.k0, b.width, b.a_off, b.b_off) for b in rq]
     with pytest.raises(ValueError):
         capi.summa_schedule_mkn(600, 1081, 792, 2, 4, 0, 0)
+
+
+def test_short_first_chunk_schedule(capi):
+    """Multi-rank objects start with a short K chunk (nothing can overlap the transfer of the first chunk): the chunks still
+    tile [0, K) exactly, only the first one is shortened, and every rank of the grid sees the same chunk boundaries."""
+    N, kc, kf = 32768, 8192, 2048
+    ref = None
+    for pi in range(2):
+        for pj in range(4):
+            steps = capi.summa_schedule_first(N, N, N, 2, 4, pi, pj, kc, kf)
+            bounds = [(s.k0, s.width) for s in steps]
+            assert bounds[0] == (0, kf) and bounds[1] == (kf, kc - kf) and all(w == kc for _, w in bounds[2:])
+            assert sum(w for _, w in bounds) == N and all(a + w == b for (a, w), (b, _) in zip(bounds, bounds[1:]))
+            ref = ref or bounds
+            assert bounds == ref
+            own = [s for s in steps if s.own_a]
+            offs = [s.a_off for s in own]
+            assert offs == sorted(offs) and offs[0] == 0  # owned chunks are stored back to back in step order
+    assert [(s.k0, s.width) for s in capi.summa_schedule_first(N, N, N, 2, 4, 0, 0, kc, 0)] == [(s.k0, s.width) for s in capi.summa_schedule(N, 2, 4, 0, 0, kc)[0]]

@@ -118,6 +118,17 @@ def test_nccl_broadcast_transport_equals_pull_transport(gpu, oracle, tmp_path):
     assert oracle.rel_frobenius(a[1], b[1]) <= 1e-14
 
 
+def test_prefetch_all_schedule_equals_default(gpu, oracle, tmp_path):
+    """PHPC_SCHEDULE=prefetch-all (stationary C, every panel transfer issued up front into a ring that holds
+    all chunks) moves the same chunks into the same GEMMs in the same order: bit-identical to the 3-slot ring."""
+    _need(gpu, 2)
+    grid = (2, 2) if gpu.phpc_b200_device_count() >= 4 else (1, 2)
+    a, _ = _run(grid, 384, 1, tmp_path, kc=50)
+    b, log = _run(grid, 384, 1, tmp_path, kc=50, env={"PHPC_SCHEDULE": "prefetch-all"})
+    for idx in (0, 2, 3, 4):
+        assert np.array_equal(a[idx], b[idx]), idx
+
+
 def test_mpi_gather_path_equals_nvlink_gather(gpu, oracle, tmp_path):
     _need(gpu, 2)
     a, _ = _run((1, 2), 256, 1, tmp_path)
