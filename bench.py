@@ -611,7 +611,7 @@ def product_arm(args):
                 roof["traffic"] = tr[0]
                 roof["traffic_source"] = (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch of {tr[2]} at m,k,n = "
                                           f"{m_blk},{k_launch},{n_blk} ({tr[1]}); algorithmic bytes of that launch: "
-                                          f"{(m_blk + n_blk) * k_launch * slices + 4 * 8 * m_blk * n_blk} (digits read once + 2 passes of C read+write); with a "
+                                          f"{(m_blk + n_blk) * k_launch * slices + 2 * 8 * m_blk * n_blk} (digits read once + one read and one write of C); with a "
                                           "126 MB L2 each wave of 148 tiles has to stream its 16 + ~9 digit panels once: 443 waves x ~25 panels x 12 MiB "
                                           "= 146 GB is the floor of this tiling")
                 roof.pop("traffic_note", None)
