@@ -113,9 +113,10 @@ struct BandBackend {
                  int host_to_device);
   void *(*record)(void *self, int stream);
   void (*wait)(void *self, int stream, void *event);
-  /* c[rows x n, ldc] += a[rows x width, lda] * b[width x n, ldb]; returns the number of kernels launched */
+  /* c[rows x n, ldc] += a[rows x width, lda] * b[width x n, ldb]; returns the number of kernels launched.  `step` = K chunk:
+   * every band multiplies by the same B chunk, so a backend may keep what it derives from B (the tcgen05 path: its digits) */
   int (*gemm)(void *self, int stream, const double *a, long long lda, const double *b, long long ldb, double *c, long long ldc, int rows,
-              int width, int n);
+              int width, int n, int step);
   /* count doubles at dst = 0  /  dst[i] += src[i] for i < count (device memory, contiguous) */
   void (*zero)(void *self, int stream, double *dst, size_t count);
   void (*add)(void *self, int stream, double *dst, const double *src, size_t count);
@@ -163,7 +164,7 @@ inline int band_execute(const BandGeom &g, const phpc_host_op *ops, int nops, co
         const phpc_summa_step &q = g.steps[o.step];
         const long long ld = band_pad_ld(q.width);
         launches += be.gemm(be.self, o.stream, g.dA + q.a_off + (size_t)o.row0 * ld, ld, g.dB + q.b_off, g.ldn,
-                            g.dC + (size_t)o.row0 * g.ldn, g.ldn, o.rows, q.width, g.n);
+                            g.dC + (size_t)o.row0 * g.ldn, g.ldn, o.rows, q.width, g.n, o.step);
         break;
       }
       case PHPC_HOP_DOWNLOAD_C:

@@ -110,6 +110,7 @@ __global__ void guard_kernel(const int *__restrict__ eA, const int *__restrict__
     int mx = ZERO_EXP, mn = EXP_NONE, sp = 0;
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
       const int v = e[i];
+      if (v == NONFINITE_EXP) atomicOr(guard, GUARD_NONFINITE); /* also set by the exponent kernels; exponents of a cached B chunk only pass here */
       if (v == ZERO_EXP || v == NONFINITE_EXP) continue;
       mx = max(mx, v);
       mn = min(mn, v);
@@ -209,8 +210,8 @@ __global__ void split_a_kernel(const double *__restrict__ A, long long lda, int 
 }
 
 __global__ void split_b_kernel(const double *__restrict__ B, long long ldb, int k, int n, int n_pad, int kp, const int *__restrict__ eB,
-                               int8_t *__restrict__ TB, const int *__restrict__ guard) {
-  if (*guard != 0) return;
+                               int8_t *__restrict__ TB, const int *__restrict__ guard /* may be NULL: split unconditionally */) {
+  if (guard && *guard != 0) return;
   split_b_body(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y, B, ldb, k, n, n_pad, kp, eB, TB);
 }
 

@@ -454,10 +454,18 @@ __global__ void guard_count_kernel(int *g) { /* g[0] = guard of the chunk, g[1] 
   }
 }
 
+size_t phpc_ozaki_bcache_bytes(int k, int n, size_t *exp_ints) {
+  using namespace phpc::oz;
+  const size_t n_pad = (size_t)((n + BN - 1) / BN) * BN, kp = (size_t)((k + 127) / 128) * 128;
+  if (exp_ints) *exp_ints = 2 * (size_t)n;
+  return (size_t)S * n_pad * kp;
+}
+
 int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
-                      int k, int n, int ctas, cudaStream_t stream) {
+                      int k, int n, int ctas, cudaStream_t stream, OzBCache *bcache) {
   using namespace phpc::oz;
   if (m <= 0 || n <= 0 || k <= 0) return 0;
+  if (bcache && k > KC_MAX) bcache = nullptr; /* the cache describes ONE K chunk */
   PHPC_REQUIRE(lda >= k && ldb >= n && ldc >= n, "leading dimension smaller than the row length");
   gemm_order_begin(ctx, stream);
   int launches = 0;
@@ -480,20 +488,23 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     const int kc = (k - k0 < KC_MAX) ? k - k0 : KC_MAX;
     const int kp = (kc + 127) / 128 * 128;
     int8_t *TA = (int8_t *)phpc_buf_reserve(&ctx->ozA, (size_t)S * m_pad * kp);
-    int8_t *TB = (int8_t *)phpc_buf_reserve(&ctx->ozB, (size_t)S * n_pad * kp);
-    int *eA = (int *)phpc_buf_reserve(&ctx->ozE, 2 * ((size_t)m + n) * sizeof(int)); /* maxima of A, of B, then the minima */
-    int *eB = eA + m, *eminA = eA + m + n, *eminB = eminA + m;
+    int8_t *TB = bcache ? bcache->TB : (int8_t *)phpc_buf_reserve(&ctx->ozB, (size_t)S * n_pad * kp);
+    int *eA = (int *)phpc_buf_reserve(&ctx->ozE, 2 * ((size_t)m + n) * sizeof(int)); /* A: maxima then minima; B likewise behind them */
+    int *eminA = eA + m;
+    int *eB = bcache ? bcache->eB : eA + 2 * (size_t)m, *eminB = eB + n;
+    const bool b_ready = bcache && bcache->ready; /* exponents and digits of this B chunk were computed by an earlier call */
     unsigned int *wave_sync = (unsigned int *)phpc_buf_reserve(&ctx->ozSync, (waves + 1) * sizeof(unsigned int));
     const double *a = dA + k0;
     const double *b = dB + (long long)k0 * ldb;
     CUDA_CHECK(cudaMemsetAsync(wave_sync, 0, (waves + 1) * sizeof(unsigned int), stream));
-    exp_init_kernel<<<(2 * (m + n) + 255) / 256, 256, 0, stream>>>(eA, m + n, guard);
+    exp_init_kernel<<<(2 * m + 255) / 256, 256, 0, stream>>>(eA, m, guard);
+    if (!b_ready) exp_init_kernel<<<(2 * n + 255) / 256, 256, 0, stream>>>(eB, n, guard);
     {
       const int segs = (kc + 1023) / 1024;
       const long long units = (long long)m * segs;
       row_exp_kernel<<<(unsigned)((units + 7) / 8), 256, 0, stream>>>(a, lda, m, kc, eA, eminA, guard);
       dim3 cgrid((n + 255) / 256, (kc + 63) / 64);
-      col_exp_kernel<<<cgrid, 256, 0, stream>>>(b, ldb, kc, n, eB, eminB, guard);
+      if (!b_ready) col_exp_kernel<<<cgrid, 256, 0, stream>>>(b, ldb, kc, n, eB, eminB, guard);
       guard_kernel<<<1, 1024, 0, stream>>>(eA, eminA, m, eB, eminB, n, guard);
       guard_count_kernel<<<1, 1, 0, stream>>>(guard);
     }
@@ -501,7 +512,9 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
       const long long threads = (long long)m_pad * (kp / 16);
       dim3 bgrid((unsigned)((n_pad + 127) / 128), kp / 32);
       split_a_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(a, lda, m, (int)m_pad, kc, kp, eA, TA, guard);
-      split_b_kernel<<<bgrid, 128, 0, stream>>>(b, ldb, kc, n, (int)n_pad, kp, eB, TB, guard);
+      /* a cached B chunk is split whatever THIS call's guard says: a later call with other A rows may take the tcgen05 path */
+      if (!b_ready) split_b_kernel<<<bgrid, 128, 0, stream>>>(b, ldb, kc, n, (int)n_pad, kp, eB, TB, bcache ? nullptr : guard);
+      if (bcache) bcache->ready = true;
     }
     Params p;
     p.C = dC;
@@ -526,7 +539,7 @@ int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const dou
     ozaki_gemm_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(p);
     CUDA_CHECK(cudaGetLastError());
     /* the same chunk on the native-FP64 kernel, which only runs when the guard is set (and the kernel above returned at once) */
-    launches += 8 + launch_dmma_guarded(ctx, a, lda, b, ldb, dC, ldc, m, kc, n, ctas, stream, guard);
+    launches += (b_ready ? 6 : 9) + launch_dmma_guarded(ctx, a, lda, b, ldb, dC, ldc, m, kc, n, ctas, stream, guard);
   }
   gemm_order_end(ctx, stream);
   return launches;

@@ -68,8 +68,17 @@ int phpc_launch_dmma(DeviceCtx *ctx, const double *dA, long long lda, const doub
                      int k, int n, int ctas, cudaStream_t stream);
 /* FP64 GEMM rebuilt from int8 tcgen05 MMAs (Ozaki scheme, 7 balanced base-256 digits per operand; K chunks the guard
  * rejects run on the DMMA kernel); returns the number of kernels launched */
+/* Exponents and digits of ONE B chunk (k <= 8192) kept by the caller across calls that multiply different A rows by the same
+ * chunk (the row bands of the host-sourced runs): the first call fills it (`ready` false), later calls skip the exponent and
+ * split kernels of B.  TB: phpc_ozaki_bcache_bytes(k, n, &ints) bytes, eB: `ints` ints.  All calls on one stream. */
+struct OzBCache {
+  signed char *TB = nullptr;
+  int *eB = nullptr;
+  bool ready = false;
+};
+size_t phpc_ozaki_bcache_bytes(int k, int n, size_t *exp_ints);
 int phpc_launch_ozaki(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
-                      int k, int n, int ctas, cudaStream_t stream);
+                      int k, int n, int ctas, cudaStream_t stream, OzBCache *bcache = nullptr);
 bool phpc_use_ozaki(void); /* env PHPC_GEMM=ozaki */
 void phpc_launch_cublas(DeviceCtx *ctx, const double *dA, long long lda, const double *dB, long long ldb, double *dC, long long ldc, int m,
                         int k, int n, cudaStream_t stream);

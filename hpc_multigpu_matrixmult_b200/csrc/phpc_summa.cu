@@ -63,9 +63,11 @@ static int env_int(const char *name, int dflt) {
 /* ------------------------------------------------------------------------- */
 /* kc_first > 0: the very first chunk (of panel 0) is only kc_first wide.  Nothing can overlap the transfer of the first chunk
  * (every rank waits for it, and up to c - 1 peers pull it from one owner at once), so it is kept small; its short GEMM then
- * covers the transfer of the first full-size chunk. */
-static int summa_schedule(int M, int K, int N, int r, int c, int pi, int pj, int kc, int kc_first, phpc_summa_step *steps, int max_steps,
-                          int *m_out, int *n_out) {
+ * covers the transfer of the next chunk.  With grow_pct > 100 the following chunks of panel 0 grow by that factor
+ * (rounded up to 128) until they reach kc: the single-GPU host-sourced run, where the upload of chunk q+1 (PCIe) is only ~25 %
+ * faster than the GEMM of chunk q, so a jump from a short chunk to a full one would expose most of the full chunk's upload. */
+static int summa_schedule(int M, int K, int N, int r, int c, int pi, int pj, int kc, int kc_first, int grow_pct, phpc_summa_step *steps,
+                          int max_steps, int *m_out, int *n_out) {
   if (M <= 0 || K <= 0 || N <= 0 || r <= 0 || c <= 0 || M % r || N % c) return -1;
   if (M <= 0 || K <= 0 || N <= 0 || r <= 0 || c <= 0 || M % r || N % c) return -1;
   const int lcm = r / gcd_int(r, c) * c;
@@ -81,9 +83,15 @@ static int summa_schedule(int M, int K, int N, int r, int c, int pi, int pj, int
     const int a_root = k % c, b_root = k % r; /* reference :64-65 */
     const int own_a = (a_root == pj), own_b = (b_root == pi);
     const int b_local_panel = k / r; /* how many panels this row owned before k (own_b) */
+    int ramp = (k == 0) ? kc_first : 0;
     for (int k_in = 0, width = 0; k_in < pk; k_in += width) {
       width = (pk - k_in < kc) ? pk - k_in : kc;
-      if (k == 0 && k_in == 0 && kc_first > 0 && kc_first < width) width = kc_first;
+      if (ramp > 0 && ramp < width) {
+        width = ramp;
+        ramp = grow_pct > 100 ? (int)(((long long)ramp * grow_pct / 100 + 127) / 128 * 128) : 0;
+      } else {
+        ramp = 0;
+      }
       if (steps && count < max_steps) {
         phpc_summa_step *s = &steps[count];
         s->panel = k;
@@ -105,12 +113,12 @@ static int summa_schedule(int M, int K, int N, int r, int c, int pi, int pj, int
 
 extern "C" int phpc_summa_schedule_mkn(int M, int K, int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps,
                                        int *m_out, int *n_out) {
-  return summa_schedule(M, K, N, r, c, pi, pj, kc, 0, steps, max_steps, m_out, n_out);
+  return summa_schedule(M, K, N, r, c, pi, pj, kc, 0, 0, steps, max_steps, m_out, n_out);
 }
 
 extern "C" int phpc_summa_schedule_first(int M, int K, int N, int r, int c, int pi, int pj, int kc, int kc_first, phpc_summa_step *steps,
                                          int max_steps, int *m_out, int *n_out) {
-  return summa_schedule(M, K, N, r, c, pi, pj, kc, kc_first, steps, max_steps, m_out, n_out);
+  return summa_schedule(M, K, N, r, c, pi, pj, kc, kc_first, 0, steps, max_steps, m_out, n_out);
 }
 
 extern "C" int phpc_summa_schedule(int N, int r, int c, int pi, int pj, int kc, phpc_summa_step *steps, int max_steps, int *m_out,
@@ -179,7 +187,8 @@ static void nccl_grid_get(MPI_Comm grid_comm, int size, int rank, int r, int c, 
 struct phpc_summa {
   MPI_Comm grid_comm;
   int rank, size;
-  int kc_first = 0;                       /* width of the very first K chunk on a multi-rank grid (0 = like the others) */
+  int kc_first = 0;                       /* width of the very first K chunk (0 = like the others) */
+  int grow_pct = 0;                       /* > 100: the chunks after it grow by this factor until they reach kc (one-rank host runs) */
   int N, r, c, pi, pj, lcm, m, n, pk, kc; /* N = global columns of B and C (= leading dimension of host B, C) */
   int gM, gK;                             /* global rows of A and C, global K (= leading dimension of host A); square: all N */
   long long ldn;   /* padded leading dimension of B chunks and of C */
@@ -210,6 +219,11 @@ struct phpc_summa {
   std::vector<cudaEvent_t> ev_c0, ev_band;     /* per band: caller's C band uploaded / band final in HBM */
   std::vector<cudaEvent_t> ev_bg0, ev_bg1;     /* per (band, step): GEMM start / stop of the banded run */
   cudaStream_t d2h[2] = {nullptr, nullptr};    /* downloads of finished bands: own C, rank 0's shared C */
+  /* banded host-sourced runs multiply every row band by the same B chunks: exponents and digits of B chunk q are computed by
+   * the first band and kept for the others (tcgen05 path; 7 bytes per element of the rank's B columns over all of K) */
+  std::vector<OzBCache> bcache;
+  signed char *bcache_tb = nullptr;
+  int *bcache_e = nullptr;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_user = nullptr, ev_cup = nullptr;
 };
 
@@ -223,9 +237,17 @@ static int pick_device(int rank) {
   return rank % count;
 }
 
-extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) { return phpc_summa_create_mkn(grid_comm, n, n, n, kc); }
+static phpc_summa *summa_create(MPI_Comm grid_comm, int gm, int gk, int n, int kc, int kc_first_single, int grow_pct_single);
+
+extern "C" phpc_summa *phpc_summa_create(MPI_Comm grid_comm, int n, int kc) { return summa_create(grid_comm, n, n, n, kc, 0, 0); }
 
 extern "C" phpc_summa *phpc_summa_create_mkn(MPI_Comm grid_comm, int gm, int gk, int n, int kc) {
+  return summa_create(grid_comm, gm, gk, n, kc, 0, 0);
+}
+
+/* kc_first_single / grow_pct_single: short first chunk and growth of the following ones on a ONE-rank grid (the host-sourced
+ * entry points ask for 1024 / 133 %); multi-rank grids always start with one short chunk (PHPC_KC_FIRST, 2048) */
+static phpc_summa *summa_create(MPI_Comm grid_comm, int gm, int gk, int n, int kc, int kc_first_single, int grow_pct_single) {
   phpc_summa *s = new phpc_summa();
   s->grid_comm = grid_comm;
   int dims[2], periods[2], coords[2];
@@ -254,11 +276,15 @@ extern "C" phpc_summa *phpc_summa_create_mkn(MPI_Comm grid_comm, int gm, int gk,
   s->lda_k = phpc_pad_ld(kc);
 
   if (s->size > 1 && kc >= 4096) s->kc_first = env_int("PHPC_KC_FIRST", 2048) / 128 * 128;
-  const int kf = s->kc_first;
-  const int nsteps = summa_schedule(gm, gk, n, s->r, s->c, s->pi, s->pj, kc, kf, nullptr, 0, nullptr, nullptr);
+  if (s->size == 1 && kc_first_single > 0 && kc >= 2 * kc_first_single) {
+    s->kc_first = kc_first_single / 128 * 128;
+    s->grow_pct = grow_pct_single;
+  }
+  const int kf = s->kc_first, gp = s->grow_pct;
+  const int nsteps = summa_schedule(gm, gk, n, s->r, s->c, s->pi, s->pj, kc, kf, gp, nullptr, 0, nullptr, nullptr);
   PHPC_REQUIRE(nsteps > 0, "empty SUMMA schedule");
   s->steps.resize(nsteps);
-  summa_schedule(gm, gk, n, s->r, s->c, s->pi, s->pj, kc, kf, s->steps.data(), nsteps, nullptr, nullptr);
+  summa_schedule(gm, gk, n, s->r, s->c, s->pi, s->pj, kc, kf, gp, s->steps.data(), nsteps, nullptr, nullptr);
 
   double t0 = now_s();
   phpc_b200_set_device(pick_device(s->rank));
@@ -302,12 +328,12 @@ extern "C" phpc_summa *phpc_summa_create_mkn(MPI_Comm grid_comm, int gm, int gk,
   {
     std::vector<phpc_summa_step> tmp(nsteps);
     for (int pj2 = 0; pj2 < s->c; ++pj2) {
-      summa_schedule(gm, gk, n, s->r, s->c, s->pi, pj2, kc, kf, tmp.data(), nsteps, nullptr, nullptr);
+      summa_schedule(gm, gk, n, s->r, s->c, s->pi, pj2, kc, kf, gp, tmp.data(), nsteps, nullptr, nullptr);
       for (int q = 0; q < nsteps; ++q)
         if (tmp[q].own_a) s->root_a_off[q] = tmp[q].a_off;
     }
     for (int pi2 = 0; pi2 < s->r; ++pi2) {
-      summa_schedule(gm, gk, n, s->r, s->c, pi2, s->pj, kc, kf, tmp.data(), nsteps, nullptr, nullptr);
+      summa_schedule(gm, gk, n, s->r, s->c, pi2, s->pj, kc, kf, gp, tmp.data(), nsteps, nullptr, nullptr);
       for (int q = 0; q < nsteps; ++q)
         if (tmp[q].own_b) s->root_b_off[q] = tmp[q].b_off;
     }
@@ -463,6 +489,8 @@ extern "C" void phpc_summa_destroy(phpc_summa *s) {
   if (s->ringB) cudaFree(s->ringB);
   if (s->gather_stage) cudaFree(s->gather_stage);
   if (s->dC0) cudaFree(s->dC0);
+  if (s->bcache_tb) cudaFree(s->bcache_tb);
+  if (s->bcache_e) cudaFree(s->bcache_e);
   for (cudaEvent_t e : s->ev_bcast) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_free) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_g0) cudaEventDestroy(e);
@@ -774,14 +802,45 @@ extern "C" void phpc_summa_run(phpc_summa *s, int backend, int ctas, void *user_
 /* ------------------------------------------------------------------------- */
 /* band-pipelined host-sourced run, one GPU                                   */
 /* ------------------------------------------------------------------------- */
+/* start of a banded run: B is about to be uploaded again, nothing derived from it is valid */
+static void bcache_arm(phpc_summa *s, int backend) {
+  if (backend != PHPC_BACKEND_OZAKI) {
+    s->bcache.clear();
+    return;
+  }
+  const int nsteps = (int)s->steps.size();
+  if (!s->bcache_tb) {
+    size_t bytes = 0, ints = 0;
+    for (const phpc_summa_step &st : s->steps) {
+      size_t e = 0;
+      bytes += phpc_ozaki_bcache_bytes(st.width, s->n, &e);
+      ints += e;
+    }
+    CUDA_CHECK(cudaMalloc(&s->bcache_tb, bytes));
+    CUDA_CHECK(cudaMalloc(&s->bcache_e, ints * sizeof(int)));
+  }
+  s->bcache.assign(nsteps, OzBCache());
+  size_t off = 0, eoff = 0;
+  for (int q = 0; q < nsteps; ++q) {
+    size_t e = 0;
+    s->bcache[q].TB = s->bcache_tb + off;
+    s->bcache[q].eB = s->bcache_e + eoff;
+    s->bcache[q].ready = false;
+    off += phpc_ozaki_bcache_bytes(s->steps[q].width, s->n, &e);
+    eoff += e;
+  }
+}
+
 static int launch_local_gemm(phpc_summa *s, int backend, int ctas, const double *a, long long lda, const double *b, double *c, int rows,
-                             int width, cudaStream_t st) {
+                             int width, cudaStream_t st, int step = -1) {
   DeviceCtx *ctx = s->ctx;
   if (backend == PHPC_BACKEND_CUBLAS) {
     phpc_launch_cublas(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, st);
     return 1;
   }
-  if (backend == PHPC_BACKEND_OZAKI) return phpc_launch_ozaki(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, ctas, st);
+  if (backend == PHPC_BACKEND_OZAKI)
+    return phpc_launch_ozaki(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, ctas, st,
+                             (step >= 0 && step < (int)s->bcache.size()) ? &s->bcache[step] : nullptr);
   return phpc_launch_dmma(ctx, a, lda, b, s->ldn, c, s->ldn, rows, width, s->n, ctas, st);
 }
 
@@ -814,7 +873,7 @@ static void cb_wait(void *self, int stream, void *event) {
   CUDA_CHECK(cudaStreamWaitEvent(b->streams[stream], (cudaEvent_t)event, 0));
 }
 static int cb_gemm(void *self, int stream, const double *a, long long lda, const double *bm, long long ldb, double *c, long long ldc,
-                   int rows, int width, int n) {
+                   int rows, int width, int n, int step) {
   CudaBandBackend *b = (CudaBandBackend *)self;
   (void)ldb;
   (void)ldc;
@@ -823,7 +882,7 @@ static int cb_gemm(void *self, int stream, const double *a, long long lda, const
   CUDA_CHECK(cudaEventCreate(&e0));
   CUDA_CHECK(cudaEventCreate(&e1));
   CUDA_CHECK(cudaEventRecord(e0, b->streams[stream]));
-  const int launches = launch_local_gemm(b->s, b->backend, b->ctas, a, lda, bm, c, rows, width, b->streams[stream]);
+  const int launches = launch_local_gemm(b->s, b->backend, b->ctas, a, lda, bm, c, rows, width, b->streams[stream], step);
   CUDA_CHECK(cudaEventRecord(e1, b->streams[stream]));
   b->g0.push_back(e0);
   b->g1.push_back(e1);
@@ -850,6 +909,7 @@ static void summa_run_host_banded(phpc_summa *s, int backend, int ctas, const do
   std::vector<phpc_host_op> ops(nops);
   phpc::host_plan(s->m, nsteps, bands, 128, ops.data(), nops);
 
+  bcache_arm(s, backend);
   CudaBandBackend cb;
   cb.s = s;
   cb.backend = backend;
@@ -956,6 +1016,7 @@ static void summa_run_host_multi_banded(phpc_summa *s, int backend, int ctas, co
     shared_base = (char *)phpc_host_shared_map(sh.name, sh.bytes, blk_off, blk_len) + blk_off;
   }
 
+  bcache_arm(s, backend);
   CUDA_CHECK(cudaEventRecord(s->ev_begin, comp));
   for (cudaStream_t st : {comm, comm2, copy, s->d2h[0], s->d2h[1]}) CUDA_CHECK(cudaStreamWaitEvent(st, s->ev_begin, 0));
   CUDA_CHECK(cudaMemsetAsync(s->dC, 0, s->c_elems * sizeof(double), comp));
@@ -1027,7 +1088,7 @@ static void summa_run_host_multi_banded(phpc_summa *s, int backend, int ctas, co
     const double *a = st.own_a ? s->dA + st.a_off + (size_t)row0 * lda : s->ringA + (size_t)slot * s->ringA_elems;
     const double *bm = st.own_b ? s->dB + st.b_off : s->ringB + (size_t)slot * s->ringB_elems;
     CUDA_CHECK(cudaEventRecord(s->ev_bg0[g], comp));
-    launches += launch_local_gemm(s, backend, ctas, a, lda, bm, s->dC + (size_t)row0 * s->ldn, rows, st.width, comp);
+    launches += launch_local_gemm(s, backend, ctas, a, lda, bm, s->dC + (size_t)row0 * s->ldn, rows, st.width, comp, q);
     CUDA_CHECK(cudaEventRecord(s->ev_bg1[g], comp));
     CUDA_CHECK(cudaEventRecord(s->ev_free[slot], comp));
     while (issued < total && issued < g + s->nbuf) stage_in(issued++);
@@ -1254,7 +1315,7 @@ static void summa_host(MPI_Comm grid_comm, const double *A, const double *B, dou
   }
   if (!s) {
     /* K chunks of 2048 columns even on one GPU: the uploads pipeline under the GEMMs */
-    s = g_host_plan = phpc_summa_create(grid_comm, n, env_int("PHPC_KC", phpc_use_ozaki() ? 4096 : 2048));
+    s = g_host_plan = summa_create(grid_comm, n, n, n, env_int("PHPC_KC", phpc_use_ozaki() ? 4096 : 2048), 1024, 133);
   }
   phpc_summa_stats stats;
   phpc_summa_run_host(s, backend, ctas, A, B, C, 1, &stats);

@@ -45,7 +45,7 @@ void sim_wait(void *self, int stream, void *event) {
   s->queue[stream].push_back({[]() {}, (const Event *)event});
 }
 int sim_gemm(void *self, int stream, const double *a, long long lda, const double *b, long long ldb, double *c, long long ldc, int rows,
-             int width, int n) {
+             int width, int n, int /* step */) {
   Sim *s = (Sim *)self;
   s->queue[stream].push_back({[=]() {
                                 for (int i = 0; i < rows; ++i)
