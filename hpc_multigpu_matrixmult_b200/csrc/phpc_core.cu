@@ -160,7 +160,10 @@ extern "C" void phpc_b200_set_device(int device) {
 extern "C" int phpc_b200_get_device(void) { return phpc_cur_ctx()->device; }
 extern "C" int phpc_b200_sm_count(void) { return phpc_cur_ctx()->sm_count; }
 
+void phpc_host_shared_release_imports(void);
+
 extern "C" void phpc_b200_finalize(void) {
+  phpc_host_shared_release_imports();
   for (int d = 0; d < PHPC_MAX_DEVICES; ++d) {
     DeviceCtx *ctx = &g_ctx[d];
     if (!ctx->ready) continue;
@@ -284,12 +287,35 @@ int phpc_host_shared_lookup(const void *p, char *name, unsigned long long *offse
 
 /* importer side: map another rank's shared allocation (cached by name); [off, off + len) of it is page-locked for this
  * process' GPU on first use */
+struct PinnedRange {
+  std::string name;
+  size_t lo, hi;
+};
+static std::vector<PinnedRange> g_pinned;
+
+/* importer side: drop every mapping of other ranks' shared allocations (their memory is only returned to the system once the
+ * last mapping is gone); called when the cached SUMMA object is released and at finalize */
+void phpc_host_shared_release_imports(void) {
+  for (size_t i = 0; i < g_shared.size();) {
+    if (g_shared[i].owner) {
+      ++i;
+      continue;
+    }
+    for (size_t j = 0; j < g_pinned.size();) {
+      if (g_pinned[j].name == g_shared[i].name) {
+        cudaHostUnregister((char *)g_shared[i].base + g_pinned[j].lo);
+        g_pinned.erase(g_pinned.begin() + j);
+      } else {
+        ++j;
+      }
+    }
+    munmap(g_shared[i].base, g_shared[i].bytes);
+    g_shared.erase(g_shared.begin() + i);
+  }
+}
+
 void *phpc_host_shared_map(const char *name, unsigned long long bytes, unsigned long long off, unsigned long long len) {
-  struct Pinned {
-    std::string name;
-    size_t lo, hi;
-  };
-  static std::vector<Pinned> pinned;
+  std::vector<PinnedRange> &pinned = g_pinned;
   void *base = nullptr;
   for (const SharedHost &h : g_shared)
     if (h.name == name) base = h.base;
@@ -301,12 +327,23 @@ void *phpc_host_shared_map(const char *name, unsigned long long bytes, unsigned 
     PHPC_REQUIRE(base != MAP_FAILED, "cannot map the shared host allocation of the gather root");
     g_shared.push_back({base, (size_t)bytes, name, false});
   }
-  const size_t lo = off / 4096 * 4096, hi = (off + len + 4095) / 4096 * 4096 < bytes ? (off + len + 4095) / 4096 * 4096 : bytes;
+  size_t lo = off / 4096 * 4096, hi = (off + len + 4095) / 4096 * 4096 < bytes ? (off + len + 4095) / 4096 * 4096 : bytes;
   bool have = false;
-  for (const Pinned &q : pinned)
+  for (const PinnedRange &q : pinned)
     if (q.name == name && q.lo <= lo && q.hi >= hi) have = true;
   if (!have) {
     phpc_cur_ctx();
+    /* a range may only be registered once: merge with whatever of this allocation is pinned already and overlaps or touches */
+    for (size_t i = 0; i < pinned.size();) {
+      if (pinned[i].name == name && pinned[i].lo <= hi && pinned[i].hi >= lo) {
+        CUDA_CHECK(cudaHostUnregister((char *)base + pinned[i].lo));
+        lo = pinned[i].lo < lo ? pinned[i].lo : lo;
+        hi = pinned[i].hi > hi ? pinned[i].hi : hi;
+        pinned.erase(pinned.begin() + i);
+      } else {
+        ++i;
+      }
+    }
     CUDA_CHECK(cudaHostRegister((char *)base + lo, hi - lo, cudaHostRegisterPortable));
     pinned.push_back({name, lo, hi});
   }

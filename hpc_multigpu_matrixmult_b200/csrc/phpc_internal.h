@@ -86,5 +86,6 @@ void phpc_launch_cublas(DeviceCtx *ctx, const double *dA, long long lda, const d
 /* shared host allocations (phpc_host_malloc_shared): owner-side lookup and importer-side mapping, used by the gather */
 int phpc_host_shared_lookup(const void *p, char *name, unsigned long long *offset, unsigned long long *bytes);
 void *phpc_host_shared_map(const char *name, unsigned long long bytes, unsigned long long off, unsigned long long len);
+void phpc_host_shared_release_imports(void);
 
 static inline long long phpc_pad_ld(long long cols) { return (cols + 15) / 16 * 16; }

@@ -1301,6 +1301,7 @@ static phpc_summa *g_host_plan = nullptr;
 extern "C" void phpc_summa_release_cache(void) {
   if (g_host_plan) phpc_summa_destroy(g_host_plan);
   g_host_plan = nullptr;
+  phpc_host_shared_release_imports(); /* mappings of rank 0's shared result matrix */
 }
 
 static void summa_host(MPI_Comm grid_comm, const double *A, const double *B, double *C, int n, int backend, int ctas, float *seconds) {
