@@ -139,6 +139,7 @@ extern "C" int phpc_host_plan(int m, int nsteps, int bands, int align, phpc_host
 struct NcclGrid {
   bool ready = false;
   int size = 0, r = 0, c = 0, rank = 0;
+  unsigned generation = 0; /* bumped whenever the communicators are rebuilt (registrations die with them) */
   ncclComm_t world = nullptr, row = nullptr, col = nullptr; /* row: same pi, rank = pj; col: same pj, rank = pi */
 };
 static NcclGrid g_nccl;
@@ -148,7 +149,9 @@ static void nccl_grid_release() {
   if (g_nccl.row) ncclCommDestroy(g_nccl.row);
   if (g_nccl.col) ncclCommDestroy(g_nccl.col);
   if (g_nccl.world) ncclCommDestroy(g_nccl.world);
+  const unsigned gen = g_nccl.generation + 1;
   g_nccl = NcclGrid();
+  g_nccl.generation = gen;
 }
 
 static void nccl_grid_get(MPI_Comm grid_comm, int size, int rank, int r, int c, int pi, int pj) {
@@ -199,6 +202,13 @@ struct phpc_summa {
   size_t a_elems = 0, b_elems = 0, c_elems = 0;
   int nbuf = 0;
   double *ringA = nullptr, *ringB = nullptr; /* nbuf receive buffers each */
+  /* PHPC_NCCL_REGISTER=1: stores and rings registered with the row / column communicator (ncclCommRegister) */
+  struct NcclReg {
+    ncclComm_t comm;
+    void *handle;
+  };
+  std::vector<NcclReg> nccl_regs;
+  unsigned nccl_generation = 0;
   double *gather_stage = nullptr;            /* rank 0: two C-block landing buffers for the gather */
   double *dC0 = nullptr;                     /* multi-rank host-sourced runs: the caller's C block, uploaded under the loop and added at the end */
   /* panel transport: 0 = ncclBroadcast on row/column communicators, 1 = copy-engine pull from the
@@ -420,6 +430,25 @@ static phpc_summa *summa_create(MPI_Comm grid_comm, int gm, int gk, int n, int k
     s->ringB_elems = (size_t)kc * s->ldn;
     CUDA_CHECK(cudaMalloc(&s->ringB, s->ringB_elems * s->nbuf * sizeof(double)));
   }
+  if (s->size > 1 && s->transport == 0 && env_int("PHPC_NCCL_REGISTER", 0)) {
+    /* User-buffer registration of everything a broadcast reads or writes: with registered buffers on every rank NCCL can
+     * move the panel straight between the user buffers over NVLink instead of through its own staging FIFOs.  Opt-in. */
+    auto reg = [&](ncclComm_t comm, double *buf, size_t elems) {
+      if (!comm || !buf || !elems) return;
+      void *h = nullptr;
+      NCCL_CHECK(ncclCommRegister(comm, buf, elems * sizeof(double), &h));
+      s->nccl_regs.push_back({comm, h});
+    };
+    s->nccl_generation = g_nccl.generation;
+    if (s->c > 1) {
+      reg(g_nccl.row, s->dA, s->a_elems);
+      reg(g_nccl.row, s->ringA, s->ringA_elems * s->nbuf);
+    }
+    if (s->r > 1) {
+      reg(g_nccl.col, s->dB, s->b_elems);
+      reg(g_nccl.col, s->ringB, s->ringB_elems * s->nbuf);
+    }
+  }
   s->ev_bcast.resize(s->nbuf);
   s->ev_bcast2.resize(s->nbuf);
   s->ev_free.resize(s->nbuf);
@@ -482,6 +511,8 @@ extern "C" void phpc_summa_destroy(phpc_summa *s) {
     MPI_Barrier(s->grid_comm); /* every importer has unmapped before the exporter frees */
   }
   for (cudaEvent_t e : s->ev_bcast2) cudaEventDestroy(e);
+  if (g_nccl.ready && s->nccl_generation == g_nccl.generation) /* else the communicators (and the registrations) are gone */
+    for (const phpc_summa::NcclReg &g : s->nccl_regs) ncclCommDeregister(g.comm, g.handle);
   cudaFree(s->dA);
   cudaFree(s->dB);
   cudaFree(s->dC);

@@ -118,6 +118,17 @@ def test_nccl_broadcast_transport_equals_pull_transport(gpu, oracle, tmp_path):
     assert oracle.rel_frobenius(a[1], b[1]) <= 1e-14
 
 
+def test_nccl_registered_buffers_equal_pull_transport(gpu, tmp_path):
+    """PHPC_NCCL_REGISTER=1: stores and receive rings registered with the row / column communicators
+    (ncclCommRegister). Registration changes how NCCL moves the bytes, never the bytes."""
+    _need(gpu, 2)
+    grid = (2, 2) if gpu.phpc_b200_device_count() >= 4 else (1, 2)
+    a, _ = _run(grid, 384, 1, tmp_path, kc=50)
+    b, _ = _run(grid, 384, 1, tmp_path, kc=50, env={"PHPC_PANEL": "nccl", "PHPC_NCCL_REGISTER": "1"})
+    for idx in (0, 2, 3):
+        assert np.array_equal(a[idx], b[idx]), idx
+
+
 def test_prefetch_all_schedule_equals_default(gpu, oracle, tmp_path):
     """PHPC_SCHEDULE=prefetch-all (stationary C, every panel transfer issued up front into a ring that holds
     all chunks) moves the same chunks into the same GEMMs in the same order: bit-identical to the 3-slot ring."""
